@@ -1,0 +1,54 @@
+// C-ABI plumbing: error reporting and dispatch between the arithmetic arms.
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+#include "../../include/demucs_b200.h"
+
+static thread_local char g_err[512] = "";
+
+void bd_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int bd_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    bd_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return BD_ERR_CUDA;
+  }
+  return BD_OK;
+}
+
+int bd_conv_gemm_simt(const bd_gemm_desc* d, void* stream);
+int bd_conv_gemm_tc(const bd_gemm_desc* d, void* stream, int* handled);
+int bd_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
+                      int ldk, int ldv, int ldo, void* stream);
+
+extern "C" {
+
+const char* bd_last_error(void) { return g_err; }
+int bd_version(void) { return 1; }
+
+int bd_conv_gemm(const bd_gemm_desc* d, void* stream) {
+  if (!d) {
+    bd_set_error("bd_conv_gemm: null descriptor");
+    return BD_ERR_ARG;
+  }
+  if (d->math == BD_MATH_TF32) {
+    int handled = 0;
+    int rc = bd_conv_gemm_tc(d, stream, &handled);
+    if (rc != BD_OK || handled) return rc;
+  }
+  return bd_conv_gemm_simt(d, stream);
+}
+
+int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
+                 int ldk, int ldv, int ldo, int math, void* stream) {
+  (void)math;
+  return bd_attention_simt(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,323 @@
+// K3/K4/K7 (exact-fp32 arm): implicit-GEMM convolution / linear kernel on the CUDA cores.
+//
+// One kernel covers every contraction of the HTDemucs forward (see bd_gemm_desc in
+// include/demucs_b200.h): the im2col gather, zero padding, A-side GroupNorm+GELU or item
+// normalisation, bias, GELU/GLU, frequency embedding, LayerScale+residual, skip add, the
+// transposed-conv scatter+crop and the GroupNorm statistics of the result are all fused, so each
+// layer reads its input once and writes its output once.
+//
+// This is the bit-faithful fp32 arm (FFMA, fp32 accumulate) used in "fp32" mode, for the
+// HBM-bound layers (C_in <= 8, DConv hidden widths 6..48) whose K or N is too small to feed a
+// tensor-core tile, and as the on-device cross-check of the tcgen05 arm (gemm_tc.cu).
+#include "common.cuh"
+#include "../../include/demucs_b200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int NTHREADS = 256;
+
+struct RowInfo {
+  long long xbase;   // b * xs_b
+  int j1, j0;        // i1*m1, i0*m0
+  int b;
+  int slab;
+  bool valid;
+};
+
+template <int BN, int TN>
+__global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_desc d, int slab_len, int tiles_per_slab) {
+  constexpr int TM = 8;
+  constexpr int TX = BN / TN;          // threads along N
+  static_assert(TX * (BM / TM) == NTHREADS, "thread layout");
+  constexpr int BPT = BN * BK / NTHREADS;  // weight elements per thread per k-tile
+  constexpr int APAD = 4, BPAD = 4;
+  __shared__ __align__(16) float As[2][BK][BM + APAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + BPAD];
+  __shared__ double red[64];
+
+  const int tid = threadIdx.x;
+  const int slab = blockIdx.x / tiles_per_slab;
+  const int tile = blockIdx.x - slab * tiles_per_slab;
+  const int n0 = blockIdx.y * BN;
+  const long long m_tile = (long long)slab * slab_len + (long long)tile * BM;
+  const int rows_left = slab_len - tile * BM;  // rows of this tile inside the slab
+
+  // ---- per-thread A gather role: one row, 8 consecutive k -------------------------------------
+  const int arow = tid & (BM - 1);
+  const int akg = (tid >> 7) * 8;
+  RowInfo ri;
+  {
+    long long m = m_tile + arow;
+    ri.valid = arow < rows_left && m < d.M;
+    long long mm = ri.valid ? m : 0;
+    int i0 = (int)(mm % d.I0);
+    long long t = mm / d.I0;
+    int i1 = (int)(t % d.I1);
+    ri.b = (int)(t / d.I1);
+    ri.xbase = ri.b * d.xs_b;
+    ri.j1 = i1 * d.m1;
+    ri.j0 = i0 * d.m0;
+    ri.slab = (int)(mm / d.I0);
+  }
+  float a_mean = 0.f, a_rstd = 1.f;
+  if (d.a_mode == BD_A_GN_GELU && ri.valid) {
+    a_mean = d.a_stats[2 * (size_t)ri.slab];
+    a_rstd = d.a_stats[2 * (size_t)ri.slab + 1];
+  } else if (d.a_mode == BD_A_ITEM_AFFINE && ri.valid) {
+    a_mean = d.a_stats[(size_t)ri.b * d.a_stats_stride];
+    a_rstd = d.a_stats[(size_t)ri.b * d.a_stats_stride + 2];
+  }
+  const bool vec8 = (d.Cin % 8 == 0) && d.xs_c == 1;
+  const bool vec4 = (d.Cin % 4 == 0) && d.xs_c == 1;
+
+  auto tap_ptr = [&](int tap, bool& ok) -> const float* {
+    int j1 = ri.j1 + d.d1[tap], j0 = ri.j0 + d.d0[tap];
+    ok = ri.valid && j1 >= 0 && j1 < d.J1 && j0 >= 0 && j0 < d.J0;
+    return d.x + ri.xbase + (long long)j1 * d.xs_1 + (long long)j0 * d.xs_0;
+  };
+  auto xform = [&](float v, int ci) -> float {
+    if (d.a_mode == BD_A_GN_GELU) return bd_gelu(fmaf((v - a_mean) * a_rstd, __ldg(d.a_gamma + ci), __ldg(d.a_beta + ci)));
+    if (d.a_mode == BD_A_ITEM_AFFINE) return (v - a_mean) * a_rstd;
+    return v;
+  };
+  auto load_a = [&](int k0, float* r) {
+    const int k = k0 + akg;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = 0.f;
+    if (k >= d.K) return;
+    if (vec8) {
+      int tap = k / d.Cin, ci = k - tap * d.Cin;
+      bool ok;
+      const float* p = tap_ptr(tap, ok);
+      if (ok) {
+        float4 u0 = __ldg(reinterpret_cast<const float4*>(p + ci));
+        float4 u1 = __ldg(reinterpret_cast<const float4*>(p + ci + 4));
+        r[0] = u0.x; r[1] = u0.y; r[2] = u0.z; r[3] = u0.w;
+        r[4] = u1.x; r[5] = u1.y; r[6] = u1.z; r[7] = u1.w;
+        if (d.a_mode != BD_A_NONE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r[i] = xform(r[i], ci + i);
+        }
+      }
+    } else if (vec4) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int kk = k + 4 * h;
+        if (kk >= d.K) break;
+        int tap = kk / d.Cin, ci = kk - tap * d.Cin;
+        bool ok;
+        const float* p = tap_ptr(tap, ok);
+        if (ok) {
+          float4 u = __ldg(reinterpret_cast<const float4*>(p + ci));
+          r[4 * h + 0] = u.x; r[4 * h + 1] = u.y; r[4 * h + 2] = u.z; r[4 * h + 3] = u.w;
+          if (d.a_mode != BD_A_NONE) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[4 * h + i] = xform(r[4 * h + i], ci + i);
+          }
+        }
+      }
+    } else {
+      int tap = k / d.Cin, ci = k - tap * d.Cin;
+      bool ok;
+      const float* p = tap_ptr(tap, ok);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (k + i < d.K) {
+          if (ok) r[i] = xform(__ldg(p + (long long)ci * d.xs_c), ci);
+          if (++ci == d.Cin) {
+            ci = 0;
+            ++tap;
+            if (k + i + 1 < d.K) p = tap_ptr(tap, ok);
+          }
+        }
+      }
+    }
+  };
+
+  // ---- per-thread weight load role ---------------------------------------------------------------
+  const int bn = tid % BN;
+  const int bkq = (tid / BN) * BPT;
+  const bool wvec = (d.K % 4 == 0) && (BPT % 4 == 0);
+  auto load_b = [&](int k0, float* r) {
+    const int n = n0 + bn, k = k0 + bkq;
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) r[i] = 0.f;
+    if (n >= d.N) return;
+    const float* p = d.w + (size_t)n * d.K + k;
+    if (wvec) {
+#pragma unroll
+      for (int i = 0; i < BPT; i += 4) {
+        if (k + i < d.K) {
+          float4 u = __ldg(reinterpret_cast<const float4*>(p + i));
+          r[i] = u.x; r[i + 1] = u.y; r[i + 2] = u.z; r[i + 3] = u.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < BPT; ++i)
+        if (k + i < d.K) r[i] = __ldg(p + i);
+    }
+  };
+
+  // ---- compute role --------------------------------------------------------------------------------
+  const int tx = tid % TX, ty = tid / TX;
+  // rows: two groups of 4 separated by BM/2; cols: groups of min(TN,4) separated by BN/2 when TN == 8
+  auto row_of = [&](int i) { return (i >> 2) * (BM / 2) + ty * 4 + (i & 3); };
+  constexpr int CG = TN >= 4 ? 4 : TN;         // contiguous columns per group
+  constexpr int NG = TN / CG;                  // column groups per thread
+  auto col_of = [&](int j) { return (j / CG) * (BN / NG) + tx * CG + (j % CG); };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float ra[8], rb[BPT];
+  load_a(0, ra);
+  load_b(0, rb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) As[0][akg + i][arow] = ra[i];
+#pragma unroll
+  for (int i = 0; i < BPT; ++i) Bs[0][bkq + i][bn] = rb[i];
+  __syncthreads();
+
+  const int nk = (d.K + BK - 1) / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      load_a((kt + 1) * BK, ra);
+      load_b((kt + 1) * BK, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float4 u = *reinterpret_cast<const float4*>(&As[cur][k][g * (BM / 2) + ty * 4]);
+        a[4 * g] = u.x; a[4 * g + 1] = u.y; a[4 * g + 2] = u.z; a[4 * g + 3] = u.w;
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float* p = &Bs[cur][k][g * (BN / NG) + tx * CG];
+        if constexpr (CG == 4) {
+          float4 u = *reinterpret_cast<const float4*>(p);
+          b[4 * g] = u.x; b[4 * g + 1] = u.y; b[4 * g + 2] = u.z; b[4 * g + 3] = u.w;
+        } else if constexpr (CG == 2) {
+          float2 u = *reinterpret_cast<const float2*>(p);
+          b[0] = u.x; b[1] = u.y;
+        } else {
+          b[0] = *p;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      const int nxt = cur ^ 1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[nxt][akg + i][arow] = ra[i];
+#pragma unroll
+      for (int i = 0; i < BPT; ++i) Bs[nxt][bkq + i][bn] = rb[i];
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----------------------------------------------------------------------------------------
+  const bool glu = d.act == BD_ACT_GLU;
+  const int Nout = glu ? d.N / 2 : d.N;
+  const int Cout = d.convt ? d.N / 4 : Nout;
+  double ssum = 0.0, ssq = 0.0;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int r = row_of(i);
+    const long long m = m_tile + r;
+    if (r >= rows_left || m >= d.M) continue;
+    const int i0 = (int)(m % d.I0);
+    const long long t = m / d.I0;
+    const int i1 = (int)(t % d.I1);
+    const long long b = t / d.I1;
+    const long long obase = b * d.os_b + (long long)i1 * d.os_1;
+    const int rb_row = d.rowbias ? (int)(m % d.rowbias_period) : 0;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + col_of(j);
+      if (n >= d.N) continue;
+      float v = acc[i][j] + (d.bias ? __ldg(d.bias + n) : 0.f);
+      int no = n;
+      if (glu) {
+        if (j & 1) continue;  // gate column, consumed by its even partner
+        float g = acc[i][j + (TN > 1 ? 1 : 0)] + (d.bias ? __ldg(d.bias + n + 1) : 0.f);
+        v = v * bd_sigmoid(g);
+        no = n >> 1;
+      } else if (d.act == BD_ACT_GELU) {
+        v = bd_gelu(v);
+      }
+      long long o;
+      if (d.convt) {
+        const int rr = n / Cout;
+        const int o0 = 4 * i0 + rr - 2;
+        if (o0 < 0 || o0 >= d.O0) continue;
+        no = n - rr * Cout;
+        o = obase + (long long)o0 * d.os_0 + no;
+      } else {
+        o = obase + (long long)i0 * d.os_0 + no;
+      }
+      if (d.rowbias) v += __ldg(d.rowbias + (size_t)rb_row * Nout + no);
+      if (d.resid) v = fmaf(d.scale ? __ldg(d.scale + no) : 1.f, v, __ldg(d.resid + o));
+      if (d.addend) v += __ldg(d.addend + o);
+      d.out[o] = v;
+      ssum += v;
+      ssq += (double)v * v;
+    }
+  }
+  if (d.stats_out) {
+    bd_block_sum2(ssum, ssq, red);
+    if (tid == 0) {
+      atomicAdd(&d.stats_out[2 * (size_t)slab], ssum);
+      atomicAdd(&d.stats_out[2 * (size_t)slab + 1], ssq);
+    }
+  }
+}
+
+template <int BN, int TN>
+int launch(const bd_gemm_desc& d, int slab_len, long long slabs, cudaStream_t st) {
+  int tiles_per_slab = (slab_len + BM - 1) / BM;
+  long long gx = slabs * tiles_per_slab;
+  int gy = (d.N + BN - 1) / BN;
+  if (gx > 0x7fffffffLL || gy > 65535) {
+    bd_set_error("bd_conv_gemm: grid too large (%lld x %d)", gx, gy);
+    return BD_ERR_ARG;
+  }
+  conv_gemm_simt_kernel<BN, TN><<<dim3((unsigned)gx, gy), NTHREADS, 0, st>>>(d, slab_len, tiles_per_slab);
+  return bd_check_launch("conv_gemm_simt_kernel");
+}
+
+}  // namespace
+
+int bd_conv_gemm_simt(const bd_gemm_desc* dp, void* stream) {
+  const bd_gemm_desc& d = *dp;
+  BD_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "bd_conv_gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
+  BD_REQUIRE(d.taps >= 1 && d.taps <= BD_MAX_TAPS && d.K == d.taps * d.Cin, "bd_conv_gemm: K != taps*Cin");
+  BD_REQUIRE(d.I0 > 0 && d.I1 > 0 && d.M % ((long long)d.I0 * d.I1) == 0, "bd_conv_gemm: M not a multiple of I1*I0");
+  BD_REQUIRE(d.x && d.w && d.out, "bd_conv_gemm: null tensor");
+  BD_REQUIRE(d.act != BD_ACT_GLU || (d.N % 2 == 0 && !d.convt), "bd_conv_gemm: GLU needs even N and no convt");
+  BD_REQUIRE(!d.convt || d.N % 4 == 0, "bd_conv_gemm: convt needs N = 4*Cout");
+  BD_REQUIRE(d.a_mode == BD_A_NONE || d.a_stats, "bd_conv_gemm: a_mode without a_stats");
+  BD_REQUIRE(d.a_mode != BD_A_GN_GELU || (d.a_gamma && d.a_beta && d.taps == 1), "bd_conv_gemm: GN prologue needs affine + 1 tap");
+  BD_REQUIRE(!d.rowbias || d.rowbias_period > 0, "bd_conv_gemm: rowbias without period");
+  cudaStream_t st = (cudaStream_t)stream;
+  // tiles never straddle a statistics slab when the epilogue reduces per slab
+  const bool slabbed = d.stats_out != nullptr;
+  const int slab_len = slabbed ? d.I0 : d.M;
+  const long long slabs = slabbed ? d.M / d.I0 : 1;
+  const bool glu = d.act == BD_ACT_GLU;
+  if (d.N > 64) return launch<128, 8>(d, slab_len, slabs, st);
+  if (d.N > 32) return launch<64, 4>(d, slab_len, slabs, st);
+  if (d.N > 16 || glu) return launch<32, 2>(d, slab_len, slabs, st);
+  return launch<16, 1>(d, slab_len, slabs, st);
+}

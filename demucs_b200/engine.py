@@ -1,0 +1,501 @@
+"""Host-side orchestration of the HTDemucs forward on the sm_100a kernel library.
+
+This is the Python mirror of ``HTDemucs.forward`` (reference demucs/htdemucs.py:527-660) and
+of the modules it calls -- HEncLayer / HDecLayer (hdemucs.py:123-157,304-335), DConv
+(demucs.py:86-154) and CrossTransformerEncoder (transformer.py:648-676) -- expressed as a
+sequence of C-ABI kernel launches (include/demucs_b200.h).  PyTorch is used for device
+memory and streams only; every arithmetic step runs in a hand-written kernel and there is no
+fallback: a missing library or a failing launch raises.
+
+Activations are kept "position-innermost channels-last": time branch [B, T, C], frequency
+branch [B, T, F, C].  In that layout the token order of the transformer
+``(t1 fr)`` (transformer.py:653) is the memory order, the strided k=8 convolutions and the
+transposed convolutions read / write contiguous windows, and STFT frames are contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import typing as tp
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, call, ptr
+from .config import HTDemucsConfig
+from .weights import check_state_dict
+
+MODES = ("fp32", "tf32")
+
+
+def _interleave_glu(w: torch.Tensor) -> torch.Tensor:
+    """Reorder rows [a_0..a_{C-1}, g_0..g_{C-1}] -> [a_0, g_0, a_1, g_1, ...] so that a GLU pair
+    (F.glu(z, dim=1): a * sigmoid(g), hdemucs.py:154,313; demucs.py:141) sits in adjacent columns."""
+    half = w.shape[0] // 2
+    return torch.stack([w[:half], w[half:]], dim=1).reshape(w.shape).contiguous()
+
+
+def _sin_embedding_1d(length: int, dim: int, max_period: float) -> torch.Tensor:
+    """create_sin_embedding, shift=0 (transformer.py:19-34) -> [length, dim] = [cos | sin]."""
+    pos = torch.arange(length, dtype=torch.float32)[:, None]
+    half = dim // 2
+    k = torch.arange(half, dtype=torch.float32)[None, :]
+    phase = pos / (max_period ** (k / (half - 1)))
+    return torch.cat([torch.cos(phase), torch.sin(phase)], dim=-1)
+
+
+def _sin_embedding_2d(dim: int, height: int, width: int, max_period: float) -> torch.Tensor:
+    """create_2d_sin_embedding (transformer.py:37-70) as a token table [(t1 fr), dim]."""
+    half = dim // 2
+    div = torch.exp(torch.arange(0.0, half, 2) * -(math.log(max_period) / half))
+    pw = torch.arange(0.0, width)[:, None] * div[None, :]     # [W, half/2]
+    ph = torch.arange(0.0, height)[:, None] * div[None, :]    # [H, half/2]
+    pe = torch.zeros(width, height, dim)
+    pe[:, :, 0:half:2] = torch.sin(pw)[:, None, :]
+    pe[:, :, 1:half:2] = torch.cos(pw)[:, None, :]
+    pe[:, :, half::2] = torch.sin(ph)[None, :, :]
+    pe[:, :, half + 1::2] = torch.cos(ph)[None, :, :]
+    return pe.reshape(width * height, dim)
+
+
+class PackedWeights:
+    """Reference state_dict -> kernel layouts (one-time, on the device)."""
+
+    def __init__(self, cfg: HTDemucsConfig, state: tp.Mapping[str, torch.Tensor], device):
+        check_state_dict(cfg, state)
+        self.t: tp.Dict[str, torch.Tensor] = {}
+        dev = device
+
+        def put(name, tensor):
+            self.t[name] = tensor.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        def conv_w(w):  # [Cout, Cin, k(,1)] / [Cout, Cin, kf, kt] -> [Cout, taps*Cin], tap-major
+            w = w.detach().float()
+            co, ci = w.shape[:2]
+            return w.reshape(co, ci, -1).permute(0, 2, 1).reshape(co, -1)
+
+        def convtr_w(w):  # [Cin, Cout, 8(,1)] -> [4*Cout, 2*Cin]; row r*Cout+co, col tap*Cin+ci = w[ci,co,r+4tap]
+            w = w.detach().float()
+            ci, co = w.shape[:2]
+            w = w.reshape(ci, co, 2, 4)                 # k = 4*tap + r
+            return w.permute(3, 1, 2, 0).reshape(4 * co, 2 * ci)
+
+        def dconv(prefix):
+            for d in range(cfg.dconv_depth):
+                p = f"{prefix}.dconv.layers.{d}"
+                put(f"{p}.w1", conv_w(state[f"{p}.0.weight"]))
+                put(f"{p}.b1", state[f"{p}.0.bias"])
+                put(f"{p}.g1", state[f"{p}.1.weight"])
+                put(f"{p}.be1", state[f"{p}.1.bias"])
+                put(f"{p}.w2", _interleave_glu(conv_w(state[f"{p}.3.weight"])))
+                put(f"{p}.b2", _interleave_glu(state[f"{p}.3.bias"].detach().float()))
+                put(f"{p}.g2", _interleave_glu(state[f"{p}.4.weight"].detach().float()))
+                put(f"{p}.be2", _interleave_glu(state[f"{p}.4.bias"].detach().float()))
+                put(f"{p}.scale", state[f"{p}.6.scale"])
+
+        for i in range(cfg.depth):
+            for name in ("encoder", "tencoder"):
+                p = f"{name}.{i}"
+                put(f"{p}.conv.w", conv_w(state[f"{p}.conv.weight"]))
+                put(f"{p}.conv.b", state[f"{p}.conv.bias"])
+                put(f"{p}.rewrite.w", _interleave_glu(conv_w(state[f"{p}.rewrite.weight"])))
+                put(f"{p}.rewrite.b", _interleave_glu(state[f"{p}.rewrite.bias"].detach().float()))
+                if cfg.dconv_mode & 1:
+                    dconv(p)
+            for name in ("decoder", "tdecoder"):
+                p = f"{name}.{i}"
+                put(f"{p}.rewrite.w", _interleave_glu(conv_w(state[f"{p}.rewrite.weight"])))
+                put(f"{p}.rewrite.b", _interleave_glu(state[f"{p}.rewrite.bias"].detach().float()))
+                put(f"{p}.conv_tr.w", convtr_w(state[f"{p}.conv_tr.weight"]))
+                put(f"{p}.conv_tr.b", state[f"{p}.conv_tr.bias"].detach().float().repeat(4))
+                if cfg.dconv_mode & 2:
+                    dconv(p)
+        if cfg.freq_emb:
+            # x + freq_emb_scale * (emb_scale * E[fr, c])  (htdemucs.py:577-582, hdemucs.py:60-66)
+            put("freq_emb", cfg.freq_emb * cfg.emb_scale * state["freq_emb.embedding.weight"].detach().float())
+        if cfg.bottom_channels:
+            for n in ("channel_upsampler", "channel_downsampler", "channel_upsampler_t", "channel_downsampler_t"):
+                put(f"{n}.w", state[f"{n}.weight"].detach().float().squeeze(-1))
+                put(f"{n}.b", state[f"{n}.bias"])
+        if cfg.t_layers > 0:
+            for k, v in state.items():
+                if k.startswith("crosstransformer."):
+                    put(k, v)
+
+    def __getitem__(self, k: str) -> torch.Tensor:
+        return self.t[k]
+
+    def nbytes(self) -> int:
+        return sum(v.numel() * 4 for v in self.t.values())
+
+
+class Engine:
+    """One HTDemucs model resident on one GPU."""
+
+    def __init__(self, cfg: HTDemucsConfig, state: tp.Mapping[str, torch.Tensor], device="cuda", mode: str = "fp32"):
+        cfg.validate()
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {MODES}")
+        self.cfg = cfg
+        self.mode = mode
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and _lib.TEST_HOOK is None:
+            raise _lib.KernelError("demucs_b200 runs on CUDA devices only (there is no CPU path)")
+        _lib.lib()  # fail loudly now if the extension is missing
+        self.W = PackedWeights(cfg, state, self.device)
+        self.window = torch.hann_window(cfg.nfft, periodic=True, dtype=torch.float32).to(self.device)
+        k = np.arange(cfg.nfft, dtype=np.float64)
+        tw = np.stack([np.cos(2 * np.pi * k / cfg.nfft), -np.sin(2 * np.pi * k / cfg.nfft)], axis=1)
+        self.twiddle = torch.from_numpy(tw.astype(np.float32)).to(self.device).contiguous()
+        self._bufs: tp.Dict[tp.Tuple, tp.Dict[str, torch.Tensor]] = {}
+        self._pos: tp.Dict[tp.Tuple, torch.Tensor] = {}
+        self.launches = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        if self.device.type != "cuda":
+            return 0
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _buf(self, key, name: str, numel: int, dtype=torch.float32, zero=False) -> torch.Tensor:
+        pool = self._bufs.setdefault(key, {})
+        t = pool.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(int(numel), dtype=dtype, device=self.device)
+            pool[name] = t
+        return t[:numel]
+
+    def _k(self, name: str, *args) -> None:
+        self.launches += 1
+        _lib.call(name, *args)
+
+    def _gemm(self, *, M, N, Cin, x, w, out, taps=((0, 0),), I1=1, I0=None, m1=1, m0=1, J1=1, J0=None,
+              xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
+              a_stats_stride=0, a_gamma=None, a_beta=None, act=_lib.ACT_NONE, rowbias=None, rowbias_period=0,
+              resid=None, scale=None, addend=None, convt=0, O0=0, stats_out=None, tc=True) -> None:
+        d = GemmDesc()
+        I0 = M if I0 is None else I0
+        d.M, d.N, d.K, d.Cin, d.taps = M, N, len(taps) * Cin, Cin, len(taps)
+        d.I1, d.I0, d.m1, d.m0, d.J1, d.J0 = I1, I0, m1, m0, J1, (I0 if J0 is None else J0)
+        for i, (a, b) in enumerate(taps):
+            d.d1[i], d.d0[i] = a, b
+        n_out = N // 2 if act == _lib.ACT_GLU else (N // 4 if convt else N)
+        d.xs_b, d.xs_1, d.xs_0, d.xs_c = xs[0], xs[1], (Cin if xs[2] is None else xs[2]), xs[3]
+        d.os_b, d.os_1, d.os_0 = os_[0], os_[1], (n_out if os_[2] is None else os_[2])
+        d.x, d.w, d.bias = ptr(x), ptr(w), ptr(bias)
+        d.a_mode, d.a_stats, d.a_stats_stride = a_mode, ptr(a_stats), a_stats_stride
+        d.a_gamma, d.a_beta = ptr(a_gamma), ptr(a_beta)
+        d.act, d.rowbias, d.rowbias_period = act, ptr(rowbias), rowbias_period
+        d.resid, d.scale, d.addend = ptr(resid), ptr(scale), ptr(addend)
+        d.out, d.convt, d.O0 = ptr(out), convt, O0
+        d.stats_out = ptr(stats_out)
+        d.math = _lib.MATH_TF32 if (self.mode == "tf32" and tc) else _lib.MATH_FP32
+        self._k("bd_conv_gemm", C.byref(d), self._stream())
+
+    # ------------------------------------------------------------------ blocks
+    def _dconv(self, key, prefix: str, x: torch.Tensor, B: int, I1: int, I0: int, C_: int, freq: bool, tag: str):
+        """DConv residual branch in place on x (demucs.py:86-154).  Rows are walked slab-major
+        (b, i1, i0): a slab = one GroupNorm(1) item = (b) in time, (b, fr) in frequency."""
+        cfg, W = self.cfg, self.W
+        hid = int(C_ / cfg.dconv_comp)
+        M = B * I1 * I0
+        slabs = B * I1
+        if freq:   # x is [B, T(i0), F(i1), C]
+            xs = (I0 * I1 * C_, C_, I1 * C_, 1)
+            us = (I0 * I1 * 2 * C_, 2 * C_, I1 * 2 * C_)
+        else:      # x is [B, T(i0), C], I1 == 1
+            xs = (I0 * C_, 0, C_, 1)
+            us = (I0 * 2 * C_, 0, 2 * C_)
+        h = self._buf(key, f"dconv_h{tag}", M * hid)
+        u = self._buf(key, f"dconv_u{tag}", M * 2 * C_)
+        sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64)
+        mr = self._buf(key, f"dconv_mr{tag}", 2 * slabs)
+        for dd in range(cfg.dconv_depth):
+            p = f"{prefix}.dconv.layers.{dd}"
+            dil = 2 ** dd
+            sums.zero_()
+            self._gemm(M=M, N=hid, Cin=C_, x=x, w=W[f"{p}.w1"], bias=W[f"{p}.b1"], out=h,
+                       taps=((0, -dil), (0, 0), (0, dil)), I1=I1, I0=I0, J1=I1, J0=I0, xs=xs,
+                       os_=(I1 * I0 * hid, I0 * hid, hid), stats_out=sums, tc=False)
+            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(I0 * hid), self._stream())
+            sums.zero_()
+            self._gemm(M=M, N=2 * C_, Cin=hid, x=h, w=W[f"{p}.w2"], bias=W[f"{p}.b2"], out=u,
+                       I1=I1, I0=I0, J1=I1, J0=I0, xs=(I1 * I0 * hid, I0 * hid, hid, 1), os_=us,
+                       a_mode=_lib.A_GN_GELU, a_stats=mr, a_gamma=W[f"{p}.g1"], a_beta=W[f"{p}.be1"],
+                       stats_out=sums, tc=False)
+            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(I0 * 2 * C_), self._stream())
+            self._k("bd_dconv_tail", ptr(x), ptr(u), ptr(mr), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
+                    ptr(W[f"{p}.scale"]), M, C_, I0 * I1, I1, self._stream())
+
+    def _attention_block(self, key, x, kv_src, p: str, attn: str, B: int, Tq: int, Tk: int, tag: str):
+        """x += gamma_1 * MHA(q=x_normed, k=v=kv_normed); both inputs are already layer-normed."""
+        W, D, H = self.W, self.cfg.transformer_dim, self.cfg.t_heads
+        Win, bin_ = W[f"{p}.{attn}.in_proj_weight"], W[f"{p}.{attn}.in_proj_bias"]
+        att = self._buf(key, f"att{tag}", B * Tq * D)
+        if kv_src is None:  # self attention: one packed projection
+            qkv = self._buf(key, f"qkv{tag}", B * Tq * 3 * D)
+            self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv)
+            self._k("bd_attention", ptr(qkv), qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, ptr(att),
+                    B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), self._stream())
+        else:
+            q = self._buf(key, f"q{tag}", B * Tq * D)
+            kv = self._buf(key, f"kv{tag}", B * Tk * 2 * D)
+            self._gemm(M=B * Tq, N=D, Cin=D, x=x, w=Win[:D], bias=bin_[:D], out=q)
+            self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv)
+            self._k("bd_attention", ptr(q), ptr(kv), kv.data_ptr() + 4 * D, ptr(att),
+                    B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), self._stream())
+        return att
+
+    def _math(self) -> int:
+        return _lib.MATH_TF32 if self.mode == "tf32" else _lib.MATH_FP32
+
+    def _ln(self, x, y, p: str, M: int, pos=None, period=0):
+        D = self.cfg.transformer_dim
+        self._k("bd_layer_norm", ptr(x), ptr(y), ptr(self.W[f"{p}.weight"]), ptr(self.W[f"{p}.bias"]),
+                ptr(pos), period, M, D, self._stream())
+
+    def _transformer_layer(self, key, x, other_normed, p: str, cross: bool, B: int, T: int, Tk: int, tag: str):
+        """One MyTransformerEncoderLayer / CrossTransformerEncoderLayer, norm_first, in place on x
+        (transformer.py:363-372, 495-500)."""
+        W, D, Hd = self.W, self.cfg.transformer_dim, self.cfg.ffn_dim
+        M = B * T
+        ln = self._buf(key, f"ln{tag}", M * D)
+        self._ln(x, ln, f"{p}.norm1", M)
+        att = self._attention_block(key, ln, other_normed if cross else None, p,
+                                    "cross_attn" if cross else "self_attn", B, T, Tk, tag)
+        a = "cross_attn" if cross else "self_attn"
+        self._gemm(M=M, N=D, Cin=D, x=att, w=W[f"{p}.{a}.out_proj.weight"], bias=W[f"{p}.{a}.out_proj.bias"],
+                   out=x, resid=x, scale=W[f"{p}.gamma_1.scale"])
+        self._ln(x, ln, f"{p}.norm3" if cross else f"{p}.norm2", M)
+        hbuf = self._buf(key, f"ffn{tag}", M * Hd)
+        self._gemm(M=M, N=Hd, Cin=D, x=ln, w=W[f"{p}.linear1.weight"], bias=W[f"{p}.linear1.bias"], out=hbuf,
+                   act=_lib.ACT_GELU)
+        sums = self._buf(key, f"no_sums{tag}", 2 * B, torch.float64)
+        mr = self._buf(key, f"no_mr{tag}", 2 * B)
+        sums.zero_()
+        self._gemm(M=M, N=D, Cin=Hd, x=hbuf, w=W[f"{p}.linear2.weight"], bias=W[f"{p}.linear2.bias"], out=x,
+                   resid=x, scale=W[f"{p}.gamma_2.scale"], I1=1, I0=T, J0=T, xs=(T * Hd, 0, Hd, 1),
+                   os_=(T * D, 0, D), stats_out=sums)
+        self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), B, float(T * D), self._stream())
+        self._k("bd_group_norm_apply", ptr(x), ptr(mr), ptr(W[f"{p}.norm_out.weight"]),
+                ptr(W[f"{p}.norm_out.bias"]), B, T, D, self._stream())
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, mix: torch.Tensor, taps: tp.Optional[dict] = None) -> torch.Tensor:
+        """mix [B, 2, L <= segment_length] (fp32, on self.device) -> [B, S, 2, L]."""
+        cfg, W = self.cfg, self.W
+        if mix.dim() != 3 or mix.shape[1] != cfg.audio_channels:
+            raise ValueError(f"expected mix of shape [B, {cfg.audio_channels}, L], got {tuple(mix.shape)}")
+        if mix.device != self.device or mix.dtype != torch.float32:
+            raise ValueError("mix must be a float32 tensor on the engine's device")
+        B, A, L0 = mix.shape
+        L = cfg.segment_length
+        if L0 > L:  # htdemucs.py:521-524
+            raise ValueError(f"Given length {L0} is longer than training length {L}")
+        key = (B, L)
+        st = self._stream()
+        if L0 < L:  # htdemucs.py:534-537: zero-pad on the right up to the training length
+            padded = self._buf(key, "mix_padded", B * A * L).view(B, A, L)
+            padded.zero_()
+            padded[..., :L0].copy_(mix)
+            mix = padded
+        mix = mix.contiguous()
+        S = cfg.n_sources
+        T = cfg.frames(L)
+        chans = cfg.enc_channels
+
+        def tap(name, t, fmt):
+            if taps is None:
+                return
+            if fmt == "f":    # [B,T,F,C] -> [B,C,F,T]
+                taps[name] = t.permute(0, 3, 2, 1).clone()
+            else:             # [B,T,C] -> [B,C,T]
+                taps[name] = t.permute(0, 2, 1).clone()
+
+        # ---- K1: STFT + CaC pack + normalisation statistics --------------------------------
+        spec = self._buf(key, "spec", B * T * 2048 * 4)
+        stats = self._buf(key, "item_stats", 4 * B, torch.float64)
+        norm = self._buf(key, "item_norm", 8 * B)
+        stats.zero_()
+        self._k("bd_stft_cac", ptr(mix), ptr(self.window), ptr(self.twiddle), ptr(spec), ptr(stats), B, A, L, st)
+        self._k("bd_finalize_item_norm", ptr(stats), ptr(norm), B, float(4 * 2048 * T), float(A * L), st)
+        tap("stft", spec.view(B, T, 2048, 4), "f")
+
+        # ---- encoders ------------------------------------------------------------------------
+        tl = cfg.time_lengths(L)
+        saved, saved_t = [], []
+        xf, Fin, Cin = spec, 2048, 2 * A
+        xt, Cin_t = mix, A
+        for i, Cc in enumerate(chans):
+            # time branch: Conv1d(k=8,s=4,p=2) on the right-padded signal -> GELU (hdemucs.py:131-144)
+            Tin, Tout = tl[i], tl[i + 1]
+            y = self._buf(key, "y_t", B * Tout * Cc)
+            first = i == 0
+            self._gemm(M=B * Tout, N=Cc, Cin=Cin_t, x=xt, w=W[f"tencoder.{i}.conv.w"], bias=W[f"tencoder.{i}.conv.b"],
+                       out=y, taps=tuple((0, k - 2) for k in range(8)), I1=1, I0=Tout, m0=4, J1=1, J0=Tin,
+                       xs=(A * L, 0, 1, L) if first else (Tin * Cin_t, 0, Cin_t, 1), os_=(Tout * Cc, 0, Cc),
+                       a_mode=_lib.A_ITEM_AFFINE if first else _lib.A_NONE,
+                       a_stats=norm[4:] if first else None, a_stats_stride=8, act=_lib.ACT_GELU)
+            if cfg.dconv_mode & 1:
+                self._dconv(key, f"tencoder.{i}", y, B, 1, Tout, Cc, False, "_t")
+            z = self._buf(key, f"saved_t{i}", B * Tout * Cc)
+            self._gemm(M=B * Tout, N=2 * Cc, Cin=Cc, x=y, w=W[f"tencoder.{i}.rewrite.w"],
+                       bias=W[f"tencoder.{i}.rewrite.b"], out=z, act=_lib.ACT_GLU)
+            saved_t.append(z)
+            xt, Cin_t = z, Cc
+            tap(f"tenc{i}", z.view(B, Tout, Cc), "t")
+
+            # frequency branch: Conv2d(k=(8,1),s=(4,1),p=(2,0)) -> GELU
+            Fo = Fin // 4
+            y = self._buf(key, "y_f", B * T * Fo * Cc)
+            self._gemm(M=B * T * Fo, N=Cc, Cin=Cin, x=xf, w=W[f"encoder.{i}.conv.w"], bias=W[f"encoder.{i}.conv.b"],
+                       out=y, taps=tuple((0, k - 2) for k in range(8)), I1=T, I0=Fo, m0=4, J1=T, J0=Fin,
+                       xs=(T * Fin * Cin, Fin * Cin, Cin, 1), os_=(T * Fo * Cc, Fo * Cc, Cc),
+                       a_mode=_lib.A_ITEM_AFFINE if first else _lib.A_NONE,
+                       a_stats=norm if first else None, a_stats_stride=8, act=_lib.ACT_GELU)
+            if cfg.dconv_mode & 1:
+                self._dconv(key, f"encoder.{i}", y, B, Fo, T, Cc, True, "_f")
+            z = self._buf(key, f"saved_f{i}", B * T * Fo * Cc)
+            emb = W["freq_emb"] if (first and cfg.freq_emb) else None
+            self._gemm(M=B * T * Fo, N=2 * Cc, Cin=Cc, x=y, w=W[f"encoder.{i}.rewrite.w"],
+                       bias=W[f"encoder.{i}.rewrite.b"], out=z, act=_lib.ACT_GLU,
+                       rowbias=emb, rowbias_period=Fo if emb is not None else 0)
+            saved.append(z)
+            xf, Fin, Cin = z, Fo, Cc
+            tap(f"enc{i}", z.view(B, T, Fo, Cc), "f")
+
+        Fb, Cb, T2 = Fin, chans[-1], tl[-1]
+        Mf, Mt = B * T * Fb, B * T2
+        # ping-pong buffers of the decoders, sized for their largest activation
+        dec_f_numel = B * T * max(2048 * 4 * S, 512 * chans[0])
+        dec_t_numel = B * max(L * 2 * S, tl[1] * chans[0])
+
+        # ---- cross-domain transformer ------------------------------------------------------------
+        if cfg.t_layers > 0:
+            D = cfg.transformer_dim
+            if cfg.bottom_channels:
+                x = self._buf(key, "tr_x", Mf * D)
+                xt_ = self._buf(key, "tr_xt", Mt * D)
+                self._gemm(M=Mf, N=D, Cin=Cb, x=xf, w=W["channel_upsampler.w"], bias=W["channel_upsampler.b"], out=x)
+                self._gemm(M=Mt, N=D, Cin=Cb, x=xt, w=W["channel_upsampler_t.w"], bias=W["channel_upsampler_t.b"],
+                           out=xt_)
+            else:
+                x = self._buf(key, "tr_x", Mf * D)
+                xt_ = self._buf(key, "tr_xt", Mt * D)
+                x.copy_(xf)
+                xt_.copy_(xt)
+            ct = "crosstransformer"
+            pos2d = self._pos_table(("2d", Fb, T))
+            pos1d = self._pos_table(("1d", T2))
+            self._ln(x, x, f"{ct}.norm_in", Mf, pos2d, T * Fb)
+            self._ln(xt_, xt_, f"{ct}.norm_in_t", Mt, pos1d, T2)
+            for i in range(cfg.t_layers):
+                if i % 2 == 0:
+                    self._transformer_layer(key, x, None, f"{ct}.layers.{i}", False, B, T * Fb, T * Fb, "_f")
+                    self._transformer_layer(key, xt_, None, f"{ct}.layers_t.{i}", False, B, T2, T2, "_t")
+                else:
+                    # both sides attend to the other's *pre-update* tokens (transformer.py:669-672)
+                    kf = self._buf(key, "kn_f", Mt * D)   # keys for the freq side = LN2(xt)
+                    kt = self._buf(key, "kn_t", Mf * D)   # keys for the time side = LN2_t(old x)
+                    self._ln(xt_, kf, f"{ct}.layers.{i}.norm2", Mt)
+                    self._ln(x, kt, f"{ct}.layers_t.{i}.norm2", Mf)
+                    self._transformer_layer(key, x, kf, f"{ct}.layers.{i}", True, B, T * Fb, T2, "_f")
+                    self._transformer_layer(key, xt_, kt, f"{ct}.layers_t.{i}", True, B, T2, T * Fb, "_t")
+                tap(f"xf.layer{i}", x.view(B, T, Fb, D), "f")
+                tap(f"xt.layer{i}", xt_.view(B, T2, D), "t")
+            # channel_downsampler (+ the decoder's skip add, hdemucs.py:310, fused as `addend`)
+            xd = self._buf(key, "dec_a", dec_f_numel)[: Mf * Cb]
+            xtd = self._buf(key, "dec_ta", dec_t_numel)[: Mt * Cb]
+            if cfg.bottom_channels:
+                self._gemm(M=Mf, N=Cb, Cin=D, x=x, w=W["channel_downsampler.w"], bias=W["channel_downsampler.b"],
+                           out=xd, addend=saved[-1])
+                self._gemm(M=Mt, N=Cb, Cin=D, x=xt_, w=W["channel_downsampler_t.w"],
+                           bias=W["channel_downsampler_t.b"], out=xtd, addend=saved_t[-1])
+            else:
+                torch.add(x, saved[-1], out=xd)
+                torch.add(xt_, saved_t[-1], out=xtd)
+            if taps is not None:
+                tap("bottleneck", (xd - saved[-1]).view(B, T, Fb, Cb), "f")
+                tap("bottleneck_t", (xtd - saved_t[-1]).view(B, T2, Cb), "t")
+        else:
+            xd = self._buf(key, "dec_a", dec_f_numel)[: Mf * Cb]
+            xtd = self._buf(key, "dec_ta", dec_t_numel)[: Mt * Cb]
+            torch.add(xf, saved[-1], out=xd)
+            torch.add(xt, saved_t[-1], out=xtd)
+
+        # ---- decoders ------------------------------------------------------------------------------
+        Fcur = Fb
+        names = ("dec_a", "dec_b")
+        for j in range(cfg.depth):
+            Cc = chans[cfg.depth - 1 - j]
+            last = j == cfg.depth - 1
+            Cout = 4 * S if last else Cc // 2
+            Cout_t = 2 * S if last else Cc // 2
+            skip = None if last else saved[cfg.depth - 2 - j]
+            skip_t = None if last else saved_t[cfg.depth - 2 - j]
+            # frequency: 3x3 rewrite + GLU (hdemucs.py:312-313)
+            y = self._buf(key, "y_f", B * T * Fcur * Cc)
+            taps9 = tuple((kt - 1, kf - 1) for kf in range(3) for kt in range(3))
+            self._gemm(M=B * T * Fcur, N=2 * Cc, Cin=Cc, x=xd, w=W[f"decoder.{j}.rewrite.w"],
+                       bias=W[f"decoder.{j}.rewrite.b"], out=y, taps=taps9, I1=T, I0=Fcur, J1=T, J0=Fcur,
+                       xs=(T * Fcur * Cc, Fcur * Cc, Cc, 1), os_=(T * Fcur * Cc, Fcur * Cc, Cc), act=_lib.ACT_GLU)
+            if cfg.dconv_mode & 2:
+                self._dconv(key, f"decoder.{j}", y, B, Fcur, T, Cc, True, "_f")
+            # ConvTranspose2d(k=(8,1), s=(4,1)) + crop [2:-2] + GELU (+ next skip) (hdemucs.py:326-334)
+            nxt = self._buf(key, names[(j + 1) % 2], dec_f_numel)[: B * T * 4 * Fcur * Cout]
+            self._gemm(M=B * T * (Fcur + 1), N=4 * Cout, Cin=Cc, x=y, w=W[f"decoder.{j}.conv_tr.w"],
+                       bias=W[f"decoder.{j}.conv_tr.b"], out=nxt, taps=((0, 0), (0, -1)), I1=T, I0=Fcur + 1,
+                       J1=T, J0=Fcur, xs=(T * Fcur * Cc, Fcur * Cc, Cc, 1),
+                       os_=(T * 4 * Fcur * Cout, 4 * Fcur * Cout, Cout), convt=1, O0=4 * Fcur,
+                       act=_lib.ACT_NONE if last else _lib.ACT_GELU, addend=skip)
+            if taps is not None:
+                tap(f"dec{j}", (nxt - skip if skip is not None else nxt).view(B, T, 4 * Fcur, Cout), "f")
+            xd, Fcur = nxt, 4 * Fcur
+
+            # time: k=3 rewrite + GLU, DConv, ConvTranspose1d(k=8,s=4) + crop [2:2+length] + GELU
+            Tin, Tout = tl[cfg.depth - j], tl[cfg.depth - 1 - j]
+            y = self._buf(key, "y_t", B * Tin * Cc)
+            self._gemm(M=B * Tin, N=2 * Cc, Cin=Cc, x=xtd, w=W[f"tdecoder.{j}.rewrite.w"],
+                       bias=W[f"tdecoder.{j}.rewrite.b"], out=y, taps=((0, -1), (0, 0), (0, 1)), I1=1, I0=Tin,
+                       J1=1, J0=Tin, xs=(Tin * Cc, 0, Cc, 1), os_=(Tin * Cc, 0, Cc), act=_lib.ACT_GLU)
+            if cfg.dconv_mode & 2:
+                self._dconv(key, f"tdecoder.{j}", y, B, 1, Tin, Cc, False, "_t")
+            nxt = self._buf(key, "dec_tb" if (j % 2 == 0) else "dec_ta", dec_t_numel)[: B * Tout * Cout_t]
+            self._gemm(M=B * (Tin + 1), N=4 * Cout_t, Cin=Cc, x=y, w=W[f"tdecoder.{j}.conv_tr.w"],
+                       bias=W[f"tdecoder.{j}.conv_tr.b"], out=nxt, taps=((0, 0), (0, -1)), I1=1, I0=Tin + 1,
+                       J1=1, J0=Tin, xs=(Tin * Cc, 0, Cc, 1), os_=(Tout * Cout_t, 0, Cout_t), convt=1, O0=Tout,
+                       act=_lib.ACT_NONE if last else _lib.ACT_GELU, addend=skip_t)
+            if taps is not None:
+                tap(f"tdec{j}", (nxt - skip_t if skip_t is not None else nxt).view(B, Tout, Cout_t), "t")
+            xtd = nxt
+
+        # ---- K2: de-normalise, iSTFT, overlap-add, add the time branch ---------------------------------
+        frames = self._buf(key, "frames", B * S * 2 * T * 4096)
+        out = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
+        self._k("bd_istft_frames", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), ptr(frames), B, S, T, st)
+        self._k("bd_ola_combine", ptr(frames), ptr(xtd), ptr(norm), ptr(out), B, S, T, L, L0, st)
+        if taps is not None:
+            zero_t = torch.zeros_like(xtd)
+            nrm0 = norm.clone()
+            nrm0[4::8] = 0
+            nrm0[5::8] = 0
+            only = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
+            self._k("bd_ola_combine", ptr(frames), ptr(zero_t), ptr(nrm0), ptr(only), B, S, T, L, L0, st)
+            taps["istft"] = only
+            taps["time_out"] = out - only
+        return out
+
+    def _pos_table(self, key) -> torch.Tensor:
+        t = self._pos.get(key)
+        if t is None:
+            cfg = self.cfg
+            D = cfg.transformer_dim
+            if key[0] == "2d":
+                t = _sin_embedding_2d(D, key[1], key[2], cfg.t_max_period)
+            else:
+                t = _sin_embedding_1d(key[1], D, cfg.t_max_period)
+            t = (cfg.t_weight_pos_embed * t).to(self.device).contiguous()
+            self._pos[key] = t
+        return t

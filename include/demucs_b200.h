@@ -1,0 +1,133 @@
+/* demucs_b200 -- C ABI of the sm_100a kernel library (libdemucs_b200.so).
+ *
+ * The reference (DrorT/demucs) is pure Python + PyTorch and has no FFI of its own; its
+ * boundary for this path is the Python API (demucs/api.py:53-319, demucs/apply.py:145-322,
+ * demucs/htdemucs.py:527-660).  This header declares the entry points the Python host layer
+ * (demucs_b200/engine.py) binds with ctypes, each replacing the PyTorch library calls the
+ * reference makes at the cited lines.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions: plain pointers to DEVICE memory owned by the caller, sizes as int / long long,
+ * `stream` is a cudaStream_t passed as void*.  No entry point synchronises, allocates or
+ * keeps state between calls.  Return value: 0 on success, negative on error
+ * (bd_last_error() gives the message; per thread).  All tensors are float32 unless noted.
+ *
+ * Activation layout ("position-innermost channels-last"): time branch [B, T, C], frequency
+ * branch [B, T, F, C]; C is the fastest axis.  DESIGN.md section 3 explains why.
+ */
+#ifndef DEMUCS_B200_H
+#define DEMUCS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BD_MAX_TAPS 9
+
+/* A-operand transforms applied while the implicit-GEMM gathers its rows. */
+enum { BD_A_NONE = 0, BD_A_GN_GELU = 1, BD_A_ITEM_AFFINE = 2 };
+/* Epilogue activations. BD_ACT_GLU expects interleaved (value, gate) output columns. */
+enum { BD_ACT_NONE = 0, BD_ACT_GELU = 1, BD_ACT_GLU = 2 };
+/* Arithmetic of the contraction. */
+enum { BD_MATH_FP32 = 0, BD_MATH_TF32 = 1 };
+
+/* One convolution / linear layer expressed as an implicit GEMM
+ *   out[m, n] = epilogue( sum_{tap, ci} A(m, tap, ci) * w[n, tap*Cin + ci] + bias[n] )
+ * Row m = (b * I1 + i1) * I0 + i0.  A(m, tap, ci) = x[b*xs_b + j1*xs_1 + j0*xs_0 + ci*xs_c]
+ * with j1 = i1*m1 + d1[tap], j0 = i0*m0 + d0[tap]; taps outside [0,J1) x [0,J0) read zero
+ * (the zero padding of Conv1d/Conv2d/ConvTranspose).  Covers, in the reference:
+ *   Conv1d/Conv2d k=8,s=4 (hdemucs.py:110), 1x1 rewrite (:116), dilated k=3 DConv convs
+ *   (demucs.py:138,140), decoder k=3 / 3x3 rewrite (hdemucs.py:294), ConvTranspose k=8,s=4
+ *   (hdemucs.py:287, `convt`), channel up/down-samplers (htdemucs.py:369-379) and every
+ *   nn.Linear / in_proj / out_proj of the transformer (transformer.py:365,418,506-512). */
+typedef struct bd_gemm_desc {
+  int M, N, K;
+  int Cin, taps;
+  int I1, I0;
+  int m1, m0, J1, J0;
+  int d1[BD_MAX_TAPS], d0[BD_MAX_TAPS];
+  long long xs_b, xs_1, xs_0, xs_c;
+  const float* x;
+  const float* w;      /* [N, K] row-major, K = taps*Cin */
+  const float* bias;   /* [N] or NULL */
+  /* A prologue */
+  int a_mode;
+  const float* a_stats; /* GN_GELU: [slab][2] = mean, rstd, slab = m / I0.  ITEM_AFFINE: per item b,
+                           a_stats[b*a_stats_stride + 0] = mean, [+2] = 1/(eps+std) */
+  int a_stats_stride;
+  const float* a_gamma; /* [Cin] (GN_GELU) */
+  const float* a_beta;  /* [Cin] */
+  /* epilogue, in this order: v = acc + bias; v = act(v); v += rowbias[(m % period)*Nout + n];
+   * v = resid + scale[n]*v (scale NULL -> 1); v += addend; store; accumulate stats of stored v */
+  int act;
+  const float* rowbias;
+  int rowbias_period;
+  const float* resid;
+  const float* scale;
+  const float* addend;
+  float* out;          /* out index = b*os_b + i1*os_1 + o0*os_0 + n_out */
+  long long os_b, os_1, os_0;
+  int convt;           /* 1: N = 4*Cout, r = n / Cout, o0 = 4*i0 + r - 2 (cropped transposed conv), else o0 = i0 */
+  int O0;              /* convt: valid output positions are 0 <= o0 < O0 */
+  double* stats_out;   /* [slab][2] += (sum, sumsq) of stored values, slab = m / I0; or NULL */
+  int math;            /* BD_MATH_* */
+} bd_gemm_desc;
+
+const char* bd_last_error(void);
+int bd_version(void);
+
+/* K1 (spec.py:11-27 + htdemucs.py:420-461 + hdemucs.py:23-40): mix [B,2,L] -> spec [B,T,2048,4]
+ * (T = ceil(L/1024)); stats[b*4 + {0,1,2,3}] += sum/sumsq of spec and of mix (zero them first). */
+int bd_stft_cac(const float* mix, const float* window, const float* twiddle, float* spec, double* stats,
+                int B, int A, int L, void* stream);
+/* htdemucs.py:545-554: stats -> norm[b*8 + {0..2}] = (mean, std, 1/(1e-5+std)) of spec, [+4..6] of mix. */
+int bd_finalize_item_norm(const double* stats, float* norm, int B, double n_freq, double n_time, void* stream);
+/* K2a (htdemucs.py:442-471,624-626 + spec.py:30-47): spec [B,T,2048,4S] -> frames [B,S,2,T,4096]. */
+int bd_istft_frames(const float* spec, const float* norm, const float* window, const float* twiddle, float* frames,
+                    int B, int S, int T, void* stream);
+/* K2b (htdemucs.py:449,653-659): out[B,S,2,Lout] = OLA(frames) + xt*stdt + meant; xt [B,Lseg,2S] or NULL. */
+int bd_ola_combine(const float* frames, const float* xt, const float* norm, float* out, int B, int S, int T, int Lseg,
+                   int Lout, void* stream);
+
+/* K3/K4/K7: implicit-GEMM convolution / linear layer, see bd_gemm_desc. */
+int bd_conv_gemm(const bd_gemm_desc* desc, void* stream);
+
+/* K5 (GroupNorm(1,C) demucs.py:123, MyGroupNorm transformer.py:258-268): (sum,sumsq) -> (mean, rstd),
+ * biased variance, eps 1e-5.  count = elements per slab. */
+int bd_finalize_group_stats(const double* sums, float* mean_rstd, int slabs, double count, void* stream);
+/* DConv tail (demucs.py:141-142,151-153): x[m, c] += scale[c] * GLU(GN(u))[m, c]; u [M, 2C] with
+ * interleaved (value, gate) columns; GroupNorm slab of row m =
+ * (m / rows_per_item) * slabs_per_item + m % slabs_per_item  (time: 1 slab per item; freq: one per bin). */
+int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float* gamma, const float* beta,
+                  const float* scale, long long M, int C, long long rows_per_item, int slabs_per_item, void* stream);
+/* nn.LayerNorm(C) (transformer.py:434-436,591-592,597-598) with optional additive table
+ * pos[(m % pos_period)*C + c] (positional embedding, transformer.py:655-663). y may alias x. */
+int bd_layer_norm(const float* x, float* y, const float* gamma, const float* beta, const float* pos,
+                  int pos_period, long long M, int C, void* stream);
+/* (sum, sumsq) per item of x [B, n] (for norm_out, transformer.py:372,500). */
+int bd_item_stats(const float* x, double* sums, int B, long long n, void* stream);
+/* MyGroupNorm(1) apply: x[b, t, c] = (x - mean_b) * rstd_b * gamma[c] + beta[c], in place. */
+int bd_group_norm_apply(float* x, const float* mean_rstd, const float* gamma, const float* beta, int B,
+                        long long rows_per_item, int C, void* stream);
+
+/* K6 (nn.MultiheadAttention via _sa_block/_ca_block, transformer.py:365,418,506): softmax(QK^T/8)V,
+ * head_dim 64, no mask.  q [B,Tq,ldq] / k,v [B,Tk,ldk] / o [B,Tq,ldo]; head h uses columns [64h, 64h+64). */
+int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk,
+                 int ldq, int ldk, int ldv, int ldo, int math, void* stream);
+
+/* K8 (apply.py:257-301 + utils.py:38-54): overlap-add of separated segments.
+ * The window of `length` samples is tiled by nseg segments starting at i*stride; the caller holds the
+ * forward outputs of segments [seg_first, seg_first+nseg_local) in segs [nseg_local, rows, valid]
+ * (all of them on one GPU; a contiguous block plus its left halo when sharded).  Segment i carries
+ * n_i = min(length - i*stride, seg_len) samples starting at column (valid - n_i)/2 (centre trim).
+ * For window sample n in [max(n_begin,out_shift), min(n_end,length)):
+ *   out[r*out_ld + n - out_shift] (+)= alpha * row_alpha[r] * sum_i w[n-i*stride]*seg_i / sum_i w[n-i*stride]
+ * out_shift/alpha implement the shift trick (apply.py:253-255), row_alpha the bag weights (apply.py:219-228). */
+int bd_overlap_add(const float* segs, const float* weight, float* out, int seg_first, int nseg_local, int nseg,
+                   int rows, int valid, int seg_len, int stride, long long length, long long out_ld,
+                   long long out_shift, long long n_begin, long long n_end, const float* row_alpha, float alpha,
+                   int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMUCS_B200_H */

@@ -1,0 +1,248 @@
+"""TEST INFRASTRUCTURE: a numpy restatement of the C ABI in include/demucs_b200.h.
+
+It lets the CPU test-suite exercise the product's HOST logic -- weight packing, implicit-GEMM
+descriptors, buffer plumbing, the apply_model batcher and the multi-rank sharder -- without a
+GPU, by standing in for libdemucs_b200.so behind ``demucs_b200._lib.TEST_HOOK``.  It is written
+against the header's documented semantics (not against the CUDA sources) and is never imported by
+the product.  The CUDA kernels themselves are checked by the ``-m gpu`` tests.
+"""
+import contextlib
+import ctypes as C
+import math
+
+import numpy as np
+
+from demucs_b200 import _lib
+
+
+def f32(p, n):
+    return np.ctypeslib.as_array(C.cast(C.c_void_p(p), C.POINTER(C.c_float)), shape=(int(n),))
+
+
+def f64(p, n):
+    return np.ctypeslib.as_array(C.cast(C.c_void_p(p), C.POINTER(C.c_double)), shape=(int(n),))
+
+
+def gelu(x):
+    from scipy.special import erf
+    return (0.5 * x * (1.0 + erf(x / np.sqrt(2.0)))).astype(np.float32)
+
+
+def sigmoid(x):
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(np.float32)
+
+
+def bd_stft_cac(mix, window, twiddle, spec, stats, B, A, L, stream):
+    T = (L + 1023) // 1024
+    x = f32(mix, B * A * L).reshape(B, A, L)
+    win = f32(window, 4096)
+    idx = np.arange(T)[:, None] * 1024 + np.arange(4096)[None, :] - 1536
+    idx = np.where(idx < 0, -idx, idx)
+    idx = np.where(idx >= L, 2 * (L - 1) - idx, idx)
+    z = np.fft.rfft(x[:, :, idx] * win, axis=-1)[..., :2048] / 64.0      # [B,A,T,F]
+    out = f32(spec, B * T * 2048 * 4).reshape(B, T, 2048, 2, 2)
+    out[..., 0] = z.real.transpose(0, 2, 3, 1)
+    out[..., 1] = z.imag.transpose(0, 2, 3, 1)
+    st = f64(stats, 4 * B).reshape(B, 4)
+    o64 = out.reshape(B, -1).astype(np.float64)
+    x64 = x.reshape(B, -1).astype(np.float64)
+    st[:, 0] += o64.sum(1); st[:, 1] += (o64 ** 2).sum(1)
+    st[:, 2] += x64.sum(1); st[:, 3] += (x64 ** 2).sum(1)
+
+
+def bd_finalize_item_norm(stats, norm, B, n_freq, n_time, stream):
+    st = f64(stats, 4 * B).reshape(B, 2, 2)
+    nm = f32(norm, 8 * B).reshape(B, 2, 4)
+    for which, n in ((0, n_freq), (1, n_time)):
+        mean = st[:, which, 0] / n
+        var = (st[:, which, 1] - st[:, which, 0] * mean) / (n - 1.0)
+        sd = np.sqrt(np.maximum(var, 0)).astype(np.float32)
+        nm[:, which, 0] = mean; nm[:, which, 1] = sd
+        nm[:, which, 2] = np.float32(1.0) / (np.float32(1e-5) + sd); nm[:, which, 3] = 0
+
+
+def bd_istft_frames(spec, norm, window, twiddle, frames, B, S, T, stream):
+    x = f32(spec, B * T * 2048 * 4 * S).reshape(B, T, 2048, S, 2, 2)
+    nm = f32(norm, 8 * B).reshape(B, 8)
+    x = x * nm[:, 1].reshape(B, 1, 1, 1, 1, 1) + nm[:, 0].reshape(B, 1, 1, 1, 1, 1)
+    z = (x[..., 0] + 1j * x[..., 1]).transpose(0, 3, 4, 1, 2)             # [B,S,2,T,F]
+    z = np.concatenate([z, np.zeros_like(z[..., :1])], axis=-1)
+    fr = np.fft.irfft(z, n=4096, axis=-1) * 64.0 * f32(window, 4096) / 1.5
+    f32(frames, B * S * 2 * T * 4096)[:] = fr.astype(np.float32).reshape(-1)
+
+
+def bd_ola_combine(frames, xt, norm, out, B, S, T, Lseg, Lout, stream):
+    fr = f32(frames, B * S * 2 * T * 4096).reshape(B, 2 * S, T, 4096)
+    acc = np.zeros((B, 2 * S, 1024 * (T - 1) + 4096), np.float32)
+    for t in range(T):
+        acc[..., t * 1024: t * 1024 + 4096] += fr[:, :, t]
+    res = acc[..., 1536: 1536 + Lout].copy()
+    if xt:
+        nm = f32(norm, 8 * B).reshape(B, 8)
+        x = f32(xt, B * Lseg * 2 * S).reshape(B, Lseg, 2 * S)[:, :Lout].transpose(0, 2, 1)
+        res += x * nm[:, 5].reshape(B, 1, 1) + nm[:, 4].reshape(B, 1, 1)
+    f32(out, B * 2 * S * Lout)[:] = res.reshape(-1)
+
+
+def bd_conv_gemm(dref, stream):
+    d = dref._obj
+    M, N, K, Cin = d.M, d.N, d.K, d.Cin
+    m = np.arange(M, dtype=np.int64)
+    i0 = m % d.I0
+    t = m // d.I0
+    i1 = t % d.I1
+    b = t // d.I1
+    w = f32(d.w, N * K).reshape(N, K)
+    A = np.zeros((M, K), np.float32)
+    ci = np.arange(Cin, dtype=np.int64) * d.xs_c
+    for tap in range(d.taps):
+        j1 = i1 * d.m1 + d.d1[tap]
+        j0 = i0 * d.m0 + d.d0[tap]
+        ok = (j1 >= 0) & (j1 < d.J1) & (j0 >= 0) & (j0 < d.J0)
+        base = b * d.xs_b + j1 * d.xs_1 + j0 * d.xs_0
+        idx = base[ok][:, None] + ci[None, :]
+        if idx.size:
+            x = f32(d.x, int(idx.max()) + 1)
+            vals = x[idx]
+            if d.a_mode == _lib.A_GN_GELU:
+                st = f32(d.a_stats, 2 * (M // d.I0)).reshape(-1, 2)[(m // d.I0)[ok]]
+                g, be = f32(d.a_gamma, Cin), f32(d.a_beta, Cin)
+                vals = gelu((vals - st[:, :1]) * st[:, 1:2] * g + be)
+            elif d.a_mode == _lib.A_ITEM_AFFINE:
+                nb = int(b.max()) + 1
+                st = f32(d.a_stats, nb * d.a_stats_stride).reshape(nb, d.a_stats_stride)[b[ok]]
+                vals = (vals - st[:, :1]) * st[:, 2:3]
+            A[ok, tap * Cin:(tap + 1) * Cin] = vals
+    v = A @ w.T
+    if d.bias:
+        v = v + f32(d.bias, N)
+    if d.act == _lib.ACT_GELU:
+        v = gelu(v)
+    elif d.act == _lib.ACT_GLU:
+        v = v[:, 0::2] * sigmoid(v[:, 1::2])
+    nout = v.shape[1]
+    n = np.arange(nout, dtype=np.int64)
+    if d.convt:
+        cout = N // 4
+        r, co = n // cout, n % cout
+        o0 = 4 * i0[:, None] + r[None, :] - 2
+        ok = (o0 >= 0) & (o0 < d.O0)
+        oidx = (b * d.os_b + i1 * d.os_1)[:, None] + o0 * d.os_0 + co[None, :]
+    else:
+        ok = np.ones((M, nout), bool)
+        oidx = (b * d.os_b + i1 * d.os_1 + i0 * d.os_0)[:, None] + n[None, :]
+    if d.rowbias:
+        rb = f32(d.rowbias, d.rowbias_period * nout).reshape(d.rowbias_period, nout)
+        v = v + rb[m % d.rowbias_period]
+    nmax = int(oidx[ok].max()) + 1
+    if d.resid:
+        sc = f32(d.scale, nout) if d.scale else np.ones(nout, np.float32)
+        v = np.where(ok, f32(d.resid, nmax)[np.where(ok, oidx, 0)] + sc * v, 0)
+    if d.addend:
+        v = v + np.where(ok, f32(d.addend, nmax)[np.where(ok, oidx, 0)], 0)
+    v = v.astype(np.float32)
+    f32(d.out, nmax)[oidx[ok]] = v[ok]
+    if d.stats_out:
+        slabs = M // d.I0
+        st = f64(d.stats_out, 2 * slabs).reshape(slabs, 2)
+        v64 = np.where(ok, v, 0).astype(np.float64)
+        np.add.at(st[:, 0], m // d.I0, v64.sum(1))
+        np.add.at(st[:, 1], m // d.I0, (v64 ** 2).sum(1))
+
+
+def bd_finalize_group_stats(sums, mean_rstd, slabs, count, stream):
+    s = f64(sums, 2 * slabs).reshape(slabs, 2)
+    o = f32(mean_rstd, 2 * slabs).reshape(slabs, 2)
+    mean = s[:, 0] / count
+    var = np.maximum(s[:, 1] / count - mean * mean, 0)
+    o[:, 0] = mean
+    o[:, 1] = 1.0 / np.sqrt(var + 1e-5)
+
+
+def bd_dconv_tail(x, u, mr, gamma, beta, scale, M, Cc, rows_per_item, spi, stream):
+    xv = f32(x, M * Cc).reshape(M, Cc)
+    uv = f32(u, M * 2 * Cc).reshape(M, 2 * Cc)
+    m = np.arange(M)
+    slab = (m // rows_per_item) * spi + (m % spi)
+    st = f32(mr, 2 * (int(slab.max()) + 1)).reshape(-1, 2)[slab]
+    g = (uv - st[:, :1]) * st[:, 1:2] * f32(gamma, 2 * Cc) + f32(beta, 2 * Cc)
+    xv += f32(scale, Cc) * (g[:, 0::2] * sigmoid(g[:, 1::2]))
+
+
+def bd_layer_norm(x, y, gamma, beta, pos, period, M, Cc, stream):
+    xv = f32(x, M * Cc).reshape(M, Cc).astype(np.float64)
+    mean = xv.mean(1, keepdims=True)
+    var = xv.var(1, keepdims=True)
+    o = (xv - mean) / np.sqrt(var + 1e-5) * f32(gamma, Cc) + f32(beta, Cc)
+    if pos:
+        o = o + f32(pos, period * Cc).reshape(period, Cc)[np.arange(M) % period]
+    f32(y, M * Cc)[:] = o.astype(np.float32).reshape(-1)
+
+
+def bd_group_norm_apply(x, mr, gamma, beta, B, rows, Cc, stream):
+    xv = f32(x, B * rows * Cc).reshape(B, rows, Cc)
+    st = f32(mr, 2 * B).reshape(B, 2)
+    xv[:] = (xv - st[:, 0].reshape(B, 1, 1)) * st[:, 1].reshape(B, 1, 1) * f32(gamma, Cc) + f32(beta, Cc)
+
+
+def _strided(p, B, T, ld, ncol):
+    a = f32(p, (B * T - 1) * ld + ncol)
+    return np.lib.stride_tricks.as_strided(a, shape=(B, T, ncol), strides=(T * ld * 4, ld * 4, 4))
+
+
+def bd_attention(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, math_, stream):
+    D = 64 * H
+    qv, kv, vv = _strided(q, B, Tq, ldq, D), _strided(k, B, Tk, ldk, D), _strided(v, B, Tk, ldv, D)
+    ov = _strided(o, B, Tq, ldo, D)
+    for h in range(H):
+        sl = slice(64 * h, 64 * h + 64)
+        s = np.einsum("bqd,bkd->bqk", qv[..., sl], kv[..., sl]).astype(np.float64) / 8.0
+        s = np.exp(s - s.max(-1, keepdims=True))
+        p = s / s.sum(-1, keepdims=True)
+        ov[..., sl] = np.einsum("bqk,bkd->bqd", p, vv[..., sl]).astype(np.float32)
+
+
+def bd_overlap_add(segs, weight, out, seg_first, nseg_local, nseg, rows, valid, seg_len, stride, length, out_ld,
+                   out_shift, n_begin, n_end, row_alpha, alpha, accumulate, stream):
+    sv = f32(segs, nseg_local * rows * valid).reshape(nseg_local, rows, valid)
+    w = f32(weight, seg_len)
+    n_begin, n_end = max(n_begin, out_shift), min(n_end, length)
+    if n_end <= n_begin:
+        return
+    num = np.zeros((rows, length), np.float32)
+    den = np.zeros(length, np.float32)
+    for i in range(seg_first, seg_first + nseg_local):
+        off = i * stride
+        n_i = min(length - off, seg_len)
+        lead = (valid - n_i) // 2
+        num[:, off:off + n_i] += w[:n_i] * sv[i - seg_first][:, lead:lead + n_i]
+        den[off:off + n_i] += w[:n_i]
+    ra = f32(row_alpha, rows)[:, None] if row_alpha else 1.0
+    res = (num[:, n_begin:n_end] / den[n_begin:n_end]) * np.float32(alpha) * ra
+    ov = f32(out, (rows - 1) * out_ld + n_end - out_shift)
+    ov = np.lib.stride_tricks.as_strided(ov, shape=(rows, n_end - out_shift), strides=(out_ld * 4, 4))
+    if accumulate:
+        ov[:, n_begin - out_shift:] += res
+    else:
+        ov[:, n_begin - out_shift:] = res
+
+
+TABLE = {k: v for k, v in globals().items() if k.startswith("bd_")}
+CALLS = []
+
+
+def hook(name, *args):
+    CALLS.append(name)
+    args = [a.value if isinstance(a, C.c_void_p) else a for a in args]
+    TABLE[name](*args)
+
+
+@contextlib.contextmanager
+def emulated_abi():
+    """Route demucs_b200's kernel calls to the numpy restatement for the duration of the block."""
+    prev = _lib.TEST_HOOK
+    _lib.TEST_HOOK = hook
+    try:
+        yield
+    finally:
+        _lib.TEST_HOOK = prev
