@@ -74,11 +74,19 @@ def build(verbose: bool = False, force: bool = False) -> str:
     deps = srcs + [os.path.join(CSRC, "common.cuh"),
                    os.path.join(os.path.dirname(HERE), "include", "demucs_b200.h")]
     deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
-    if not force and os.path.exists(LIB_PATH) and \
-            os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
-        return LIB_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    import hashlib
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    digest = hashlib.sha256(" ".join(flags).encode())
+    for dep in sorted(set(deps)):
+        with open(dep, "rb") as f:
+            digest.update(f.read())
+    stamp_path = LIB_PATH + ".stamp"
+    stamp = digest.hexdigest()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_path):
+        with open(stamp_path) as f:
+            if f.read().strip() == stamp:       # content hash: file times do not survive a snapshot
+                return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + flags + ["-shared", "-o", LIB_PATH] + srcs + ["-lcuda"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
@@ -88,6 +96,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
         raise KernelError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
     if verbose:
         print(res.stderr)
+    with open(stamp_path, "w") as f:
+        f.write(stamp)
     return LIB_PATH
 
 

@@ -151,6 +151,7 @@ class Engine:
         self._bufs: tp.Dict[tp.Tuple, tp.Dict[str, torch.Tensor]] = {}
         self._pos: tp.Dict[tp.Tuple, torch.Tensor] = {}
         self.launches = 0
+        self._prof: tp.Optional[list] = None
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self) -> int:
@@ -166,9 +167,18 @@ class Engine:
             pool[name] = t
         return t[:numel]
 
-    def _k(self, name: str, *args) -> None:
+    def _k(self, name: str, *args, flops: float = 0.0, nbytes: float = 0.0, label: tp.Optional[str] = None) -> None:
+        """Launch one kernel through the C ABI.  ``flops`` / ``nbytes`` are the ALGORITHMIC work of the
+        launch, recorded with CUDA events when a profile is being taken."""
         self.launches += 1
+        if self._prof is None:
+            _lib.call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         _lib.call(name, *args)
+        e1.record()
+        self._prof.append((label or name, e0, e1, flops, nbytes))
 
     def _gemm(self, *, M, N, Cin, x, w, out, taps=((0, 0),), I1=1, I0=None, m1=1, m0=1, J1=1, J0=None,
               xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
@@ -191,7 +201,14 @@ class Engine:
         d.out, d.convt, d.O0 = ptr(out), convt, O0
         d.stats_out = ptr(stats_out)
         d.math = _lib.MATH_TF32 if (self.mode == "tf32" and tc) else _lib.MATH_FP32
-        self._k("bd_conv_gemm", C.byref(d), self._stream())
+        K = len(taps) * Cin
+        rows_in = (M // (I1 * I0)) * d.J1 * d.J0          # input positions (each read once, algorithmically)
+        nbytes = 4.0 * (rows_in * Cin + N * K + M * (N if convt else n_out))
+        nbytes += 4.0 * M * n_out * ((resid is not None) + (addend is not None))
+        arm = "tc" if d.math == _lib.MATH_TF32 else "simt"
+        tile = 128 if N > 64 else 64 if N > 32 else 32 if (N > 16 or act == _lib.ACT_GLU) else 16
+        self._k("bd_conv_gemm", C.byref(d), self._stream(), flops=2.0 * M * N * K, nbytes=nbytes,
+                label=f"conv_gemm_{arm}<{tile}>")
 
     # ------------------------------------------------------------------ blocks
     def _dconv(self, key, prefix: str, x: torch.Tensor, B: int, I1: int, I0: int, C_: int, freq: bool, tag: str):
@@ -226,7 +243,7 @@ class Engine:
                        stats_out=sums, tc=False)
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(I0 * 2 * C_), self._stream())
             self._k("bd_dconv_tail", ptr(x), ptr(u), ptr(mr), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
-                    ptr(W[f"{p}.scale"]), M, C_, I0 * I1, I1, self._stream())
+                    ptr(W[f"{p}.scale"]), M, C_, I0 * I1, I1, self._stream(), nbytes=4.0 * M * C_ * 4)
 
     def _attention_block(self, key, x, kv_src, p: str, attn: str, B: int, Tq: int, Tk: int, tag: str):
         """x += gamma_1 * MHA(q=x_normed, k=v=kv_normed); both inputs are already layer-normed."""
@@ -237,14 +254,16 @@ class Engine:
             qkv = self._buf(key, f"qkv{tag}", B * Tq * 3 * D)
             self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv)
             self._k("bd_attention", ptr(qkv), qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, ptr(att),
-                    B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), self._stream())
+                    B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), self._stream(),
+                    flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label="attention")
         else:
             q = self._buf(key, f"q{tag}", B * Tq * D)
             kv = self._buf(key, f"kv{tag}", B * Tk * 2 * D)
             self._gemm(M=B * Tq, N=D, Cin=D, x=x, w=Win[:D], bias=bin_[:D], out=q)
             self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv)
             self._k("bd_attention", ptr(q), ptr(kv), kv.data_ptr() + 4 * D, ptr(att),
-                    B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), self._stream())
+                    B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), self._stream(),
+                    flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label="attention")
         return att
 
     def _math(self) -> int:
@@ -253,7 +272,7 @@ class Engine:
     def _ln(self, x, y, p: str, M: int, pos=None, period=0):
         D = self.cfg.transformer_dim
         self._k("bd_layer_norm", ptr(x), ptr(y), ptr(self.W[f"{p}.weight"]), ptr(self.W[f"{p}.bias"]),
-                ptr(pos), period, M, D, self._stream())
+                ptr(pos), period, M, D, self._stream(), nbytes=8.0 * M * D)
 
     def _transformer_layer(self, key, x, other_normed, p: str, cross: bool, B: int, T: int, Tk: int, tag: str):
         """One MyTransformerEncoderLayer / CrossTransformerEncoderLayer, norm_first, in place on x
@@ -279,7 +298,7 @@ class Engine:
                    os_=(T * D, 0, D), stats_out=sums)
         self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), B, float(T * D), self._stream())
         self._k("bd_group_norm_apply", ptr(x), ptr(mr), ptr(W[f"{p}.norm_out.weight"]),
-                ptr(W[f"{p}.norm_out.bias"]), B, T, D, self._stream())
+                ptr(W[f"{p}.norm_out.bias"]), B, T, D, self._stream(), nbytes=8.0 * B * T * D)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -319,7 +338,8 @@ class Engine:
         stats = self._buf(key, "item_stats", 4 * B, torch.float64)
         norm = self._buf(key, "item_norm", 8 * B)
         stats.zero_()
-        self._k("bd_stft_cac", ptr(mix), ptr(self.window), ptr(self.twiddle), ptr(spec), ptr(stats), B, A, L, st)
+        self._k("bd_stft_cac", ptr(mix), ptr(self.window), ptr(self.twiddle), ptr(spec), ptr(stats), B, A, L, st,
+                nbytes=4.0 * B * (A * L + T * 2048 * 4), flops=2.5 * 4096 * 12 * 2 * B * T)
         self._k("bd_finalize_item_norm", ptr(stats), ptr(norm), B, float(4 * 2048 * T), float(A * L), st)
         tap("stft", spec.view(B, T, 2048, 4), "f")
 
@@ -474,8 +494,10 @@ class Engine:
         # ---- K2: de-normalise, iSTFT, overlap-add, add the time branch ---------------------------------
         frames = self._buf(key, "frames", B * S * 2 * T * 4096)
         out = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
-        self._k("bd_istft_frames", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), ptr(frames), B, S, T, st)
-        self._k("bd_ola_combine", ptr(frames), ptr(xtd), ptr(norm), ptr(out), B, S, T, L, L0, st)
+        self._k("bd_istft_frames", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), ptr(frames), B, S, T, st,
+                nbytes=4.0 * B * T * S * (2048 * 4 + 2 * 4096), flops=2.5 * 4096 * 12 * 2 * S * B * T)
+        self._k("bd_ola_combine", ptr(frames), ptr(xtd), ptr(norm), ptr(out), B, S, T, L, L0, st,
+                nbytes=4.0 * B * S * 2 * (T * 4096 + L + L0))
         if taps is not None:
             zero_t = torch.zeros_like(xtd)
             nrm0 = norm.clone()
