@@ -87,7 +87,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
             if f.read().strip() == stamp:       # content hash: file times do not survive a snapshot
                 return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + flags + ["-shared", "-o", LIB_PATH] + srcs + ["-lcuda"]
+    cmd = [nvcc] + flags + ["-shared", "-o", LIB_PATH] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

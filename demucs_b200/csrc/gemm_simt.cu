@@ -9,8 +9,7 @@
 // This is the bit-faithful fp32 arm (FFMA, fp32 accumulate) used in "fp32" mode, for the
 // HBM-bound layers (C_in <= 8, DConv hidden widths 6..48) whose K or N is too small to feed a
 // tensor-core tile, and as the on-device cross-check of the tcgen05 arm (gemm_tc.cu).
-#include "common.cuh"
-#include "../../include/demucs_b200.h"
+#include "gemm_epilogue.cuh"
 
 namespace {
 
@@ -228,51 +227,22 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
   }
 
   // ---- epilogue ----------------------------------------------------------------------------------------
-  const bool glu = d.act == BD_ACT_GLU;
-  const int Nout = glu ? d.N / 2 : d.N;
-  const int Cout = d.convt ? d.N / 4 : Nout;
   double ssum = 0.0, ssq = 0.0;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int r = row_of(i);
     const long long m = m_tile + r;
     if (r >= rows_left || m >= d.M) continue;
-    const int i0 = (int)(m % d.I0);
-    const long long t = m / d.I0;
-    const int i1 = (int)(t % d.I1);
-    const long long b = t / d.I1;
-    const long long obase = b * d.os_b + (long long)i1 * d.os_1;
-    const int rb_row = d.rowbias ? (int)(m % d.rowbias_period) : 0;
+    const EpiRow er = bd_epi_row(d, m);
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + col_of(j);
       if (n >= d.N) continue;
-      float v = acc[i][j] + (d.bias ? __ldg(d.bias + n) : 0.f);
-      int no = n;
-      if (glu) {
-        if (j & 1) continue;  // gate column, consumed by its even partner
-        float g = acc[i][j + (TN > 1 ? 1 : 0)] + (d.bias ? __ldg(d.bias + n + 1) : 0.f);
-        v = v * bd_sigmoid(g);
-        no = n >> 1;
-      } else if (d.act == BD_ACT_GELU) {
-        v = bd_gelu(v);
+      float v;
+      if (bd_epi_apply(d, er, n, acc[i][j], acc[i][(j + 1) % TN], v)) {
+        ssum += v;
+        ssq += (double)v * v;
       }
-      long long o;
-      if (d.convt) {
-        const int rr = n / Cout;
-        const int o0 = 4 * i0 + rr - 2;
-        if (o0 < 0 || o0 >= d.O0) continue;
-        no = n - rr * Cout;
-        o = obase + (long long)o0 * d.os_0 + no;
-      } else {
-        o = obase + (long long)i0 * d.os_0 + no;
-      }
-      if (d.rowbias) v += __ldg(d.rowbias + (size_t)rb_row * Nout + no);
-      if (d.resid) v = fmaf(d.scale ? __ldg(d.scale + no) : 1.f, v, __ldg(d.resid + o));
-      if (d.addend) v += __ldg(d.addend + o);
-      d.out[o] = v;
-      ssum += v;
-      ssq += (double)v * v;
     }
   }
   if (d.stats_out) {

@@ -1,11 +1,291 @@
-// K3/K7 (tensor-core arm): tcgen05 / TMEM / TMA GEMM.  Placeholder dispatcher until the kernel lands:
-// reports "not handled" so that bd_conv_gemm falls through to the exact fp32 arm.
-#include "common.cuh"
-#include "../../include/demucs_b200.h"
+// K3/K7 (tensor-core arm): tcgen05 / TMEM / TMA GEMM for sm_100a, TF32 inputs, fp32 accumulate.
+//
+//   out[m, n] = epilogue( sum_k A[m, k] * W[n, k] )      A: activations [M, K] row-major (K-major)
+//                                                        W: weights     [N, K] row-major (K-major)
+// Both operands are K-major, so one TMA box of 32 floats x 128 rows lands in shared memory as
+// 128-byte rows in the SWIZZLE_128B pattern that the UMMA shared-memory descriptor consumes
+// directly.  One CTA computes a 128x128 tile: a 128-lane x 128-column fp32 accumulator in TMEM,
+// fed by `tcgen05.mma.cta_group::1.kind::tf32` (M=128, N=128, K=8 per instruction).
+//
+// Warp roles (192 threads):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> HBM;
+// warp w owns TMEM lanes 32*(w%4) .. +31).  Pipelines: smem full/empty mbarriers between TMA and
+// MMA (kStages deep), one tmem_full mbarrier between MMA and the epilogue.  Two CTAs fit per SM
+// (96 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps the other's main loop.
+//
+// Covered layers (taps == 1, no A-side transform): every nn.Linear of the cross-transformer
+// (transformer.py:365,418,506-512 -> in_proj, out_proj, linear1+GELU, linear2+LayerScale+residual
+// + norm_out statistics), the channel up/down-samplers (htdemucs.py:586-599) and the encoder 1x1
+// rewrite + GLU (hdemucs.py:152-154).  Everything else stays on the fp32 arm (gemm_simt.cu).
+#include <cuda.h>
+#include "gemm_epilogue.cuh"
 
-int bd_conv_gemm_tc(const bd_gemm_desc* d, void* stream, int* handled) {
-  (void)d;
-  (void)stream;
+namespace {
+
+constexpr int TBM = 128, TBN = 128, TBK = 32;      // tile (floats)
+constexpr int kStages = 3;
+constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
+constexpr int kTmemCols = 128;
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kSpinLimit = 1u << 26;          // turn a lost barrier into a trap, never a hang
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 8 rows * 128 B
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem) {
+  uint64_t desc = (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
+  desc |= (uint64_t)(1024 >> 4) << 32;
+  desc |= (uint64_t)1 << 46;
+  desc |= (uint64_t)2 << 61;
+  return desc;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=TF32, both K-major, N, M
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- kernel -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b,
+                                                                const bd_gemm_desc d, int slab_len, int tiles_per_slab) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kStageBytesA;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * kStageBytesB);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  __shared__ double red[64];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.x / tiles_per_slab;
+  const int tile = blockIdx.x - slab * tiles_per_slab;
+  const int n0 = blockIdx.y * TBN;
+  const long long m_tile = (long long)slab * slab_len + (long long)tile * TBM;
+  const int rows_left = slab_len - tile * TBM;
+  const int nkb = (d.K + TBK - 1) / TBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
+        tma_load_2d(&map_a, &full_bar[s], sA + s * kStageBytesA, kb * TBK, (int)m_tile);
+        tma_load_2d(&map_b, &full_bar[s], sB + s * kStageBytesB, kb * TBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TBM, TBN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint64_t adesc = make_kmajor_sw128_desc(sA + s * kStageBytesA);
+        const uint64_t bdesc = make_kmajor_sw128_desc(sB + s * kStageBytesB);
+#pragma unroll
+        for (int k = 0; k < TBK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B: advance the start address by 32 B >> 4
+          umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        tcgen05_commit(&empty_bar[s]);      // frees the smem stage once these MMAs have read it
+      }
+      tcgen05_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const long long m = m_tile + r;
+    const bool row_ok = r < rows_left && m < d.M;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    EpiRow er;
+    if (row_ok) er = bd_epi_row(d, m);
+    double ssum = 0.0, ssq = 0.0;
+    for (int c0 = 0; c0 < TBN; c0 += 32) {
+      if (n0 + c0 >= d.N) break;            // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < d.N) {
+            float st;
+            if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) & 31]), st)) {
+              ssum += st;
+              ssq += (double)st * st;
+            }
+          }
+        }
+      }
+    }
+    if (d.stats_out) {
+      ssum = bd_warp_sum_d(ssum);
+      ssq = bd_warp_sum_d(ssq);
+      if (lane == 0) {
+        red[quarter] = ssum;
+        red[4 + quarter] = ssq;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (d.stats_out && threadIdx.x == 0) {
+    atomicAdd(&d.stats_out[2 * (size_t)slab], red[0] + red[1] + red[2] + red[3]);
+    atomicAdd(&d.stats_out[2 * (size_t)slab + 1], red[4] + red[5] + red[6] + red[7]);
+  }
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D K-major fp32 tensor [rows, K] with row pitch `ld` floats; box = 32 x 128, 128-byte swizzle
+bool make_map(CUtensorMap* map, const float* base, long long rows, int K, long long ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
+  const bd_gemm_desc& d = *dp;
   *handled = 0;
-  return BD_OK;
+  // eligibility: a plain K-major GEMM big enough to fill tensor-core tiles
+  const bool plain = d.taps == 1 && d.a_mode == BD_A_NONE && d.xs_c == 1 && d.I1 == 1 && d.m0 == 1 && d.d0[0] == 0 &&
+                     d.d1[0] == 0 && d.J0 >= d.I0 && d.xs_b == (long long)d.I0 * d.xs_0;
+  if (!plain || d.K % 4 != 0 || d.xs_0 % 4 != 0 || d.N < 64 || d.K < 32 || d.M < 128) return BD_OK;
+  if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15)) return BD_OK;
+  BD_REQUIRE(d.act != BD_ACT_GLU || d.N % 2 == 0, "bd_conv_gemm: GLU needs even N");
+  alignas(64) CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, d.x, d.M, d.K, d.xs_0) || !make_map(&map_b, d.w, d.N, d.K, d.K)) {
+    bd_set_error("bd_conv_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d ld=%lld)", d.M, d.N, d.K, d.xs_0);
+    return BD_ERR_CUDA;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) {
+      bd_set_error("bd_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return BD_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const bool slabbed = d.stats_out != nullptr;
+  const int slab_len = slabbed ? d.I0 : d.M;
+  const long long slabs = slabbed ? d.M / d.I0 : 1;
+  const int tiles_per_slab = (slab_len + TBM - 1) / TBM;
+  dim3 grid((unsigned)(slabs * tiles_per_slab), (d.N + TBN - 1) / TBN);
+  conv_gemm_tc_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(map_a, map_b, d, slab_len, tiles_per_slab);
+  *handled = 1;
+  return bd_check_launch("conv_gemm_tc_kernel");
 }

@@ -203,3 +203,28 @@ def test_errors_are_loud():
         model(torch.zeros(1, 2, cfg.segment_length + 1, device=DEV))
     with pytest.raises(D.KernelError):
         D.HTDemucs.from_config(cfg, init_seed=0).forward(torch.zeros(1, 2, 4096))   # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("name", ["htdemucs_default.npz", "htdemucs_ls05.npz"])
+def test_forward_htdemucs_tf32_mode(name):
+    """tcgen05 TF32 arm: per-stem relative L2 <= 1e-4 against the reference golden (north_star,
+    fp32/TF32 mode), block taps within TF32 rounding."""
+    g = golden(name)
+    cfg = htdemucs_config()
+    W, mix = forward_fixture_inputs(g, cfg)
+    eng = Engine(cfg, W, DEV, mode="tf32")
+    taps = {}
+    got = eng.forward(mix.to(DEV), taps)
+    torch.cuda.synchronize()
+    errs = {}
+    for key in g.files:
+        if key.startswith("tap."):
+            errs[key[4:]] = rel_l2(strided(taps[key[4:]].contiguous(), int(g["tap_stride"])), g[key])
+    e_out = rel_l2(strided(got, int(g["stride"])), g["out"])
+    print(name, "tf32 out rel-L2", e_out, "worst tap", max(errs.items(), key=lambda kv: kv[1]))
+    assert max(errs.values()) < 3e-3
+    with torch.no_grad():
+        want = htdemucs_forward(W, cfg, mix)
+    stems = stem_errors(got.cpu(), want)
+    print("per-stem", stems)
+    assert max(stems) < STEM_TOL
