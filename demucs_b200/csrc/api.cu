@@ -24,6 +24,7 @@ int bd_check_launch(const char* what) {
 
 int bd_conv_gemm_simt(const bd_gemm_desc* d, void* stream);
 int bd_conv_gemm_tc(const bd_gemm_desc* d, void* stream, int* handled);
+bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d);
 int bd_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
                       int ldk, int ldv, int ldo, void* stream);
 
@@ -43,6 +44,10 @@ int bd_conv_gemm(const bd_gemm_desc* d, void* stream) {
     if (rc != BD_OK || handled) return rc;
   }
   return bd_conv_gemm_simt(d, stream);
+}
+
+int bd_conv_gemm_arm(const bd_gemm_desc* d) {
+  return (d && d->math == BD_MATH_TF32 && bd_conv_gemm_tc_eligible(*d)) ? 1 : 0;
 }
 
 int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,

@@ -10,15 +10,21 @@ struct EpiRow {
   int rb_row;        // m % rowbias_period
 };
 
-__device__ __forceinline__ EpiRow bd_epi_row(const bd_gemm_desc& d, long long m) {
+__device__ __forceinline__ EpiRow bd_epi_row(const bd_gemm_desc& d, long long m64) {
   EpiRow r;
-  r.i0 = (int)(m % d.I0);
-  const long long t = m / d.I0;
-  const int i1 = (int)(t % d.I1);
-  const long long b = t / d.I1;
-  r.obase = b * d.os_b + (long long)i1 * d.os_1;
-  r.rb_row = d.rowbias ? (int)(m % d.rowbias_period) : 0;
+  const unsigned m = (unsigned)m64;            // M < 2^31: 32-bit divisions
+  const unsigned t = m / (unsigned)d.I0;
+  r.i0 = (int)(m - t * (unsigned)d.I0);
+  const unsigned b = t / (unsigned)d.I1;
+  const int i1 = (int)(t - b * (unsigned)d.I1);
+  r.obase = (long long)b * d.os_b + (long long)i1 * d.os_1;
+  r.rb_row = d.rowbias ? (int)(m % (unsigned)d.rowbias_period) : 0;
   return r;
+}
+
+__device__ __forceinline__ int bd_stat_slab(const bd_gemm_desc& d, long long m64) {
+  const unsigned m = (unsigned)m64;
+  return (int)((m / (unsigned)d.stat_div) * (unsigned)d.stat_mul + (m % (unsigned)d.stat_mod));
 }
 
 // Finish accumulator `acc` of column n (and `acc_gate` of column n+1 for GLU, n even) of row `r`.
@@ -41,7 +47,7 @@ __device__ __forceinline__ bool bd_epi_apply(const bd_gemm_desc& d, const EpiRow
   if (d.convt) {
     const int Cout = d.N >> 2;
     const int rr = n / Cout;
-    const int o0 = 4 * r.i0 + rr - 2;
+    const int o0 = 4 * r.i0 + rr - (d.convt == 1 ? 2 : 0);
     if (o0 < 0 || o0 >= d.O0) return false;
     no = n - rr * Cout;
     Nout = Cout;

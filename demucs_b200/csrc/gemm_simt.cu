@@ -50,18 +50,18 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
   {
     long long m = m_tile + arow;
     ri.valid = arow < rows_left && m < d.M;
-    long long mm = ri.valid ? m : 0;
-    int i0 = (int)(mm % d.I0);
-    long long t = mm / d.I0;
-    int i1 = (int)(t % d.I1);
-    ri.b = (int)(t / d.I1);
+    const unsigned mm = ri.valid ? (unsigned)m : 0u;
+    const unsigned t = mm / (unsigned)d.I0;
+    const int i0 = (int)(mm - t * (unsigned)d.I0);
+    ri.b = (int)(t / (unsigned)d.I1);
+    const int i1 = (int)(t - (unsigned)ri.b * (unsigned)d.I1);
     ri.xbase = ri.b * d.xs_b;
     ri.j1 = i1 * d.m1;
     ri.j0 = i0 * d.m0;
-    ri.slab = (int)(mm / d.I0);
+    ri.slab = d.a_mode == BD_A_GN_GELU ? bd_stat_slab(d, mm) : 0;
   }
   float a_mean = 0.f, a_rstd = 1.f;
-  if (d.a_mode == BD_A_GN_GELU && ri.valid) {
+  if (d.a_mode == BD_A_GN_GELU && ri.valid) {  // slab map: see bd_gemm_desc
     a_mean = d.a_stats[2 * (size_t)ri.slab];
     a_rstd = d.a_stats[2 * (size_t)ri.slab + 1];
   } else if (d.a_mode == BD_A_ITEM_AFFINE && ri.valid) {
@@ -227,29 +227,52 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
   }
 
   // ---- epilogue ----------------------------------------------------------------------------------------
+  // Statistics: tiles are slab-aligned when every row of a tile shares one GroupNorm slab (stat_mod == 1);
+  // otherwise (frequency branch, slab = (b, fr) changes with every row) each row reduces across the TX
+  // threads that share it and issues its own pair of atomics.
+  const bool row_stats = d.stats_out && d.stat_mod != 1;
   double ssum = 0.0, ssq = 0.0;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int r = row_of(i);
     const long long m = m_tile + r;
-    if (r >= rows_left || m >= d.M) continue;
-    const EpiRow er = bd_epi_row(d, m);
+    const bool ok = r < rows_left && m < d.M;
+    float rs = 0.f, rq = 0.f;
+    if (ok) {
+      const EpiRow er = bd_epi_row(d, m);
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int n = n0 + col_of(j);
-      if (n >= d.N) continue;
-      float v;
-      if (bd_epi_apply(d, er, n, acc[i][j], acc[i][(j + 1) % TN], v)) {
-        ssum += v;
-        ssq += (double)v * v;
+      for (int j = 0; j < TN; ++j) {
+        const int n = n0 + col_of(j);
+        if (n >= d.N) continue;
+        float v;
+        if (bd_epi_apply(d, er, n, acc[i][j], acc[i][(j + 1) % TN], v)) {
+          rs += v;
+          rq = fmaf(v, v, rq);
+        }
       }
     }
+    if (row_stats) {   // the TX = 16 threads of a row are 16 consecutive lanes
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        rq += __shfl_xor_sync(0xffffffffu, rq, o);
+      }
+      if (ok && tx == 0) {
+        const int sl = bd_stat_slab(d, m);
+        atomicAdd(&d.stats_out[2 * (size_t)sl], (double)rs);
+        atomicAdd(&d.stats_out[2 * (size_t)sl + 1], (double)rq);
+      }
+    } else {
+      ssum += rs;
+      ssq += rq;
+    }
   }
-  if (d.stats_out) {
+  if (d.stats_out && !row_stats) {
     bd_block_sum2(ssum, ssq, red);
     if (tid == 0) {
-      atomicAdd(&d.stats_out[2 * (size_t)slab], ssum);
-      atomicAdd(&d.stats_out[2 * (size_t)slab + 1], ssq);
+      const int sl = bd_stat_slab(d, m_tile);
+      atomicAdd(&d.stats_out[2 * (size_t)sl], ssum);
+      atomicAdd(&d.stats_out[2 * (size_t)sl + 1], ssq);
     }
   }
 }
@@ -281,10 +304,13 @@ int bd_conv_gemm_simt(const bd_gemm_desc* dp, void* stream) {
   BD_REQUIRE(d.a_mode != BD_A_GN_GELU || (d.a_gamma && d.a_beta && d.taps == 1), "bd_conv_gemm: GN prologue needs affine + 1 tap");
   BD_REQUIRE(!d.rowbias || d.rowbias_period > 0, "bd_conv_gemm: rowbias without period");
   cudaStream_t st = (cudaStream_t)stream;
-  // tiles never straddle a statistics slab when the epilogue reduces per slab
-  const bool slabbed = d.stats_out != nullptr;
-  const int slab_len = slabbed ? d.I0 : d.M;
-  const long long slabs = slabbed ? d.M / d.I0 : 1;
+  BD_REQUIRE((!d.stats_out && d.a_mode != BD_A_GN_GELU) || (d.stat_div > 0 && d.stat_mul > 0 && d.stat_mod > 0),
+             "bd_conv_gemm: statistics requested without a slab map");
+  BD_REQUIRE(!d.stats_out || d.stat_mod != 1 || d.M % d.stat_div == 0, "bd_conv_gemm: M not a multiple of stat_div");
+  // tiles never straddle a statistics slab when a whole tile reduces into one slab
+  const bool slabbed = d.stats_out != nullptr && d.stat_mod == 1;
+  const int slab_len = slabbed ? d.stat_div : d.M;
+  const long long slabs = slabbed ? d.M / d.stat_div : 1;
   const bool glu = d.act == BD_ACT_GLU;
   if (d.N > 64) return launch<128, 8>(d, slab_len, slabs, st);
   if (d.N > 32) return launch<64, 4>(d, slab_len, slabs, st);

@@ -13,21 +13,41 @@
 // MMA (kStages deep), one tmem_full mbarrier between MMA and the epilogue.  Two CTAs fit per SM
 // (96 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps the other's main loop.
 //
-// Covered layers (taps == 1, no A-side transform): every nn.Linear of the cross-transformer
-// (transformer.py:365,418,506-512 -> in_proj, out_proj, linear1+GELU, linear2+LayerScale+residual
-// + norm_out statistics), the channel up/down-samplers (htdemucs.py:586-599) and the encoder 1x1
-// rewrite + GLU (hdemucs.py:152-154).  Everything else stays on the fp32 arm (gemm_simt.cu).
+// Implicit GEMM: for a multi-tap convolution the K loop walks (tap, channel block); the A tile of a
+// tap is ONE rank-4 TMA box [channels x R0 positions x R1 rows x 1 item] of the channels-last
+// activation tensor shifted by the tap offset -- out-of-range coordinates are zero-filled by the TMA
+// unit, which is exactly the convolution's zero padding, so there is no im2col buffer and no
+// boundary code.  A 128-row tile is R1 x R0 output positions (R0 = 128 for long axes, 8..64 for
+// the short frequency axes of the inner layers).
+//
+// Covered layers (unit stride, no A-side transform, C_in % 16 == 0): every nn.Linear of the
+// cross-transformer (transformer.py:365,418,506-512), the channel up/down-samplers
+// (htdemucs.py:586-599), the encoder 1x1 rewrite + GLU (hdemucs.py:152-154), the decoder 3x3 / k=3
+// rewrite + GLU (hdemucs.py:312-313) and the transposed convolutions in their 3-tap form
+// (hdemucs.py:326-334).  The stride-4 encoder convolutions, the DConv branch (HBM-bound, N or K of
+// 6..48) and C_in <= 8 layers stay on the fp32 arm (gemm_simt.cu).
 #include <cuda.h>
 #include "gemm_epilogue.cuh"
 
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 32;      // tile (floats)
-constexpr int kStages = 3;
-constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
+constexpr int TBM = 128, TBN = 128;                // tile rows / columns
 constexpr int kTmemCols = 128;
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+template <int TBK>
+struct Cfg {                                       // TBK floats per k-block: 32 -> 128B swizzle, 16 -> 64B swizzle
+  static constexpr int kStages = TBK == 32 ? 3 : 6;
+  static constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
+  static constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileGeom {
+  int R0, R1;            // tile = R1 rows (i1) x R0 positions (i0), R0 * R1 == 128, powers of two
+  int log2R0;
+  int blocks0, blocks1;  // tiles along i0 / i1 per item
+  int cpb;               // channel blocks per tap = Cin / TBK
+};
 constexpr uint32_t kSpinLimit = 1u << 26;          // turn a lost barrier into a trap, never a hang
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -52,6 +72,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (done) return;
     if (++spins > kSpinLimit) __trap();
   }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
@@ -79,11 +106,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 8 rows * 128 B
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem) {
+//   SWIZZLE_64B (16-float rows): SBO = 8 rows * 64 B, layout = 4
+template <int TBK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(const void* smem) {
   uint64_t desc = (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
-  desc |= (uint64_t)(1024 >> 4) << 32;
+  desc |= (uint64_t)((8 * TBK * 4) >> 4) << 32;
   desc |= (uint64_t)1 << 46;
-  desc |= (uint64_t)2 << 61;
+  desc |= (uint64_t)(TBK == 32 ? 2 : 4) << 61;
   return desc;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=TF32, both K-major, N, M
@@ -105,9 +134,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 // ---- kernel -------------------------------------------------------------------------------------------
+template <int TBK>
 __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
-                                                                const bd_gemm_desc d, int slab_len, int tiles_per_slab) {
+                                                                const bd_gemm_desc d, const TileGeom g) {
+  using C_ = Cfg<TBK>;
+  constexpr int kStages = C_::kStages, kStageBytesA = C_::kStageBytesA, kStageBytesB = C_::kStageBytesB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -116,15 +148,17 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  __shared__ double red[64];
+  __shared__ double red[8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slab = blockIdx.x / tiles_per_slab;
-  const int tile = blockIdx.x - slab * tiles_per_slab;
+  // tile -> (item b, row block, position block)
+  const int blk0 = blockIdx.x % g.blocks0;
+  const int tq = blockIdx.x / g.blocks0;
+  const int blk1 = tq % g.blocks1;
+  const int b = tq / g.blocks1;
+  const int i0s = blk0 * g.R0, i1s = blk1 * g.R1;
   const int n0 = blockIdx.y * TBN;
-  const long long m_tile = (long long)slab * slab_len + (long long)tile * TBM;
-  const int rows_left = slab_len - tile * TBM;
-  const int nkb = (d.K + TBK - 1) / TBK;
+  const int nkb = d.taps * g.cpb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -147,13 +181,19 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      int tap = 0, cb = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
-        tma_load_2d(&map_a, &full_bar[s], sA + s * kStageBytesA, kb * TBK, (int)m_tile);
-        tma_load_2d(&map_b, &full_bar[s], sB + s * kStageBytesB, kb * TBK, n0);
+        // A: the tap-shifted window of the activation tensor; out-of-range rows/positions read as zero
+        tma_load_4d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, i0s + d.d0[tap], i1s + d.d1[tap], b);
+        tma_load_2d(&map_b, &full_bar[s], sB + s * kStageBytesB, tap * d.Cin + cb * TBK, n0);
+        if (++cb == g.cpb) {
+          cb = 0;
+          ++tap;
+        }
       }
     }
   } else if (warp == 1) {
@@ -165,8 +205,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
-        const uint64_t adesc = make_kmajor_sw128_desc(sA + s * kStageBytesA);
-        const uint64_t bdesc = make_kmajor_sw128_desc(sB + s * kStageBytesB);
+        const uint64_t adesc = make_kmajor_desc<TBK>(sA + s * kStageBytesA);
+        const uint64_t bdesc = make_kmajor_desc<TBK>(sB + s * kStageBytesB);
 #pragma unroll
         for (int k = 0; k < TBK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B: advance the start address by 32 B >> 4
           umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -178,13 +218,14 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const long long m = m_tile + r;
-    const bool row_ok = r < rows_left && m < d.M;
+    const int i0 = i0s + (r & (g.R0 - 1)), i1 = i1s + (r >> g.log2R0);
+    const bool row_ok = i0 < d.I0 && i1 < d.I1;
+    const long long m = ((long long)b * d.I1 + i1) * d.I0 + i0;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     EpiRow er;
     if (row_ok) er = bd_epi_row(d, m);
-    double ssum = 0.0, ssq = 0.0;
+    float ssum = 0.f, ssq = 0.f;
     for (int c0 = 0; c0 < TBN; c0 += 32) {
       if (n0 + c0 >= d.N) break;            // warp-uniform
       uint32_t v[32];
@@ -197,26 +238,26 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
             float st;
             if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) & 31]), st)) {
               ssum += st;
-              ssq += (double)st * st;
+              ssq = fmaf(st, st, ssq);
             }
           }
         }
       }
     }
     if (d.stats_out) {
-      ssum = bd_warp_sum_d(ssum);
-      ssq = bd_warp_sum_d(ssq);
+      double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
       if (lane == 0) {
-        red[quarter] = ssum;
-        red[4 + quarter] = ssq;
+        red[quarter] = ds;
+        red[4 + quarter] = dq;
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (d.stats_out && threadIdx.x == 0) {
-    atomicAdd(&d.stats_out[2 * (size_t)slab], red[0] + red[1] + red[2] + red[3]);
-    atomicAdd(&d.stats_out[2 * (size_t)slab + 1], red[4] + red[5] + red[6] + red[7]);
+  if (d.stats_out && threadIdx.x == 0) {   // host guarantees one slab per tile (I1 == 1, I0 == stat_div)
+    const int sl = bd_stat_slab(d, (long long)b * d.I1 * d.I0 + i0s);
+    atomicAdd(&d.stats_out[2 * (size_t)sl], red[0] + red[1] + red[2] + red[3]);
+    atomicAdd(&d.stats_out[2 * (size_t)sl + 1], red[4] + red[5] + red[6] + red[7]);
   }
   if (warp == 1) {
     tcgen05_fence_after();
@@ -242,50 +283,88 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D K-major fp32 tensor [rows, K] with row pitch `ld` floats; box = 32 x 128, 128-byte swizzle
-bool make_map(CUtensorMap* map, const float* base, long long rows, int K, long long ld) {
+bool encode(CUtensorMap* map, const float* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes,
+            const cuuint32_t* box, int tbk) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, gdim, gstride_bytes, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, tbk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-}  // namespace
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
 
-int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
-  const bd_gemm_desc& d = *dp;
-  *handled = 0;
-  // eligibility: a plain K-major GEMM big enough to fill tensor-core tiles
-  const bool plain = d.taps == 1 && d.a_mode == BD_A_NONE && d.xs_c == 1 && d.I1 == 1 && d.m0 == 1 && d.d0[0] == 0 &&
-                     d.d1[0] == 0 && d.J0 >= d.I0 && d.xs_b == (long long)d.I0 * d.xs_0;
-  if (!plain || d.K % 4 != 0 || d.xs_0 % 4 != 0 || d.N < 64 || d.K < 32 || d.M < 128) return BD_OK;
-  if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15)) return BD_OK;
-  BD_REQUIRE(d.act != BD_ACT_GLU || d.N % 2 == 0, "bd_conv_gemm: GLU needs even N");
+template <int TBK>
+int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st) {
+  using C_ = Cfg<TBK>;
   alignas(64) CUtensorMap map_a, map_b;
-  if (!make_map(&map_a, d.x, d.M, d.K, d.xs_0) || !make_map(&map_b, d.w, d.N, d.K, d.K)) {
-    bd_set_error("bd_conv_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d ld=%lld)", d.M, d.N, d.K, d.xs_0);
+  // activations: (c, j0, j1, item); size-1 axes get a harmless contiguous stride
+  const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
+  cuuint64_t adim[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.J0, (cuuint64_t)d.J1, (cuuint64_t)items};
+  cuuint64_t astr[3] = {(cuuint64_t)s0 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)sb * 4};
+  cuuint32_t abox[4] = {(cuuint32_t)TBK, (cuuint32_t)g.R0, (cuuint32_t)g.R1, 1};
+  cuuint64_t bdim[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
+  cuuint64_t bstr[1] = {(cuuint64_t)d.K * 4};
+  cuuint32_t bbox[2] = {(cuuint32_t)TBK, (cuuint32_t)TBN};
+  if (!encode(&map_a, d.x, 4, adim, astr, abox, TBK) || !encode(&map_b, d.w, 2, bdim, bstr, bbox, TBK)) {
+    bd_set_error("bd_conv_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d Cin=%d J0=%d J1=%d)", d.M, d.N, d.K,
+                 d.Cin, d.J0, d.J1);
     return BD_ERR_CUDA;
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C_::kSmemBytes);
     if (e != cudaSuccess) {
       bd_set_error("bd_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return BD_ERR_CUDA;
     }
     configured = true;
   }
-  const bool slabbed = d.stats_out != nullptr;
-  const int slab_len = slabbed ? d.I0 : d.M;
-  const long long slabs = slabbed ? d.M / d.I0 : 1;
-  const int tiles_per_slab = (slab_len + TBM - 1) / TBM;
-  dim3 grid((unsigned)(slabs * tiles_per_slab), (d.N + TBN - 1) / TBN);
-  conv_gemm_tc_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(map_a, map_b, d, slab_len, tiles_per_slab);
-  *handled = 1;
+  dim3 grid((unsigned)((long long)items * g.blocks1 * g.blocks0), (d.N + TBN - 1) / TBN);
+  conv_gemm_tc_kernel<TBK><<<grid, kThreads, C_::kSmemBytes, st>>>(map_a, map_b, d, g);
   return bd_check_launch("conv_gemm_tc_kernel");
+}
+
+}  // namespace
+
+// eligibility: unit-stride implicit GEMM, channels-last, big enough to fill tensor-core tiles
+bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d) {
+  if (d.a_mode != BD_A_NONE || d.xs_c != 1 || d.m0 != 1 || d.m1 != 1) return false;
+  if (d.Cin % 16 != 0 || d.N < 64 || d.K < 32 || d.M < 128 || d.taps > BD_MAX_TAPS) return false;
+  if (d.xs_0 % 4 != 0 || (d.J1 > 1 && d.xs_1 % 4 != 0) || d.xs_b % 4 != 0) return false;
+  if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15)) return false;
+  if (d.stats_out && !(d.stat_mod == 1 && d.I1 == 1 && d.I0 == d.stat_div)) return false;
+  return true;
+}
+
+int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
+  const bd_gemm_desc& d = *dp;
+  *handled = 0;
+  if (!bd_conv_gemm_tc_eligible(d)) return BD_OK;
+  BD_REQUIRE(d.act != BD_ACT_GLU || d.N % 2 == 0, "bd_conv_gemm: GLU needs even N");
+  BD_REQUIRE(d.M % ((long long)d.I0 * d.I1) == 0, "bd_conv_gemm: M not a multiple of I1*I0");
+  TileGeom g;
+  g.R0 = (d.I0 >= 128 || d.I1 == 1) ? 128 : (pow2_ceil(d.I0) > 128 ? 128 : pow2_ceil(d.I0));
+  g.R1 = 128 / g.R0;
+  g.log2R0 = 0;
+  while ((1 << g.log2R0) < g.R0) ++g.log2R0;
+  g.blocks0 = (d.I0 + g.R0 - 1) / g.R0;
+  g.blocks1 = (d.I1 + g.R1 - 1) / g.R1;
+  const int items = d.M / (d.I0 * d.I1);
+  int rc;
+  if (d.Cin % 32 == 0) {
+    g.cpb = d.Cin / 32;
+    rc = launch_tc<32>(d, g, items, (cudaStream_t)stream);
+  } else {
+    g.cpb = d.Cin / 16;
+    rc = launch_tc<16>(d, g, items, (cudaStream_t)stream);
+  }
+  *handled = 1;
+  return rc;
 }

@@ -62,7 +62,7 @@ def _sin_embedding_2d(dim: int, height: int, width: int, max_period: float) -> t
 class PackedWeights:
     """Reference state_dict -> kernel layouts (one-time, on the device)."""
 
-    def __init__(self, cfg: HTDemucsConfig, state: tp.Mapping[str, torch.Tensor], device):
+    def __init__(self, cfg: HTDemucsConfig, state: tp.Mapping[str, torch.Tensor], device, tc_forms: bool = False):
         check_state_dict(cfg, state)
         self.t: tp.Dict[str, torch.Tensor] = {}
         dev = device
@@ -80,6 +80,22 @@ class PackedWeights:
             ci, co = w.shape[:2]
             w = w.reshape(ci, co, 2, 4)                 # k = 4*tap + r
             return w.permute(3, 1, 2, 0).reshape(4 * co, 2 * ci)
+
+        def convtr_w3(w):
+            """3-tap form of the same transposed conv: output row p = 4 outputs 4p+s, s<4, read x[p-1], x[p], x[p+1]:
+            u = 4p+s+2 = 4*ti + k  =>  tap -1: k=s+6 (s<=1), tap 0: k=s+2, tap +1: k=s-2 (s>=2); other entries zero.
+            Rows = input positions exactly, so tensor-core tiles carry no halo row."""
+            w = w.detach().float()
+            ci, co = w.shape[:2]
+            w = w.reshape(ci, co, 8)
+            out = torch.zeros(4, co, 3, ci)
+            for s_ in range(4):
+                out[s_, :, 1] = w[:, :, s_ + 2].t()
+                if s_ <= 1:
+                    out[s_, :, 0] = w[:, :, s_ + 6].t()
+                else:
+                    out[s_, :, 2] = w[:, :, s_ - 2].t()
+            return out.reshape(4 * co, 3 * ci)
 
         def dconv(prefix):
             for d in range(cfg.dconv_depth):
@@ -108,6 +124,8 @@ class PackedWeights:
                 put(f"{p}.rewrite.w", _interleave_glu(conv_w(state[f"{p}.rewrite.weight"])))
                 put(f"{p}.rewrite.b", _interleave_glu(state[f"{p}.rewrite.bias"].detach().float()))
                 put(f"{p}.conv_tr.w", convtr_w(state[f"{p}.conv_tr.weight"]))
+                if tc_forms:
+                    put(f"{p}.conv_tr.w3", convtr_w3(state[f"{p}.conv_tr.weight"]))
                 put(f"{p}.conv_tr.b", state[f"{p}.conv_tr.bias"].detach().float().repeat(4))
                 if cfg.dconv_mode & 2:
                     dconv(p)
@@ -143,7 +161,7 @@ class Engine:
         if self.device.type != "cuda" and _lib.TEST_HOOK is None:
             raise _lib.KernelError("demucs_b200 runs on CUDA devices only (there is no CPU path)")
         _lib.lib()  # fail loudly now if the extension is missing
-        self.W = PackedWeights(cfg, state, self.device)
+        self.W = PackedWeights(cfg, state, self.device, tc_forms=(mode == "tf32"))
         self.window = torch.hann_window(cfg.nfft, periodic=True, dtype=torch.float32).to(self.device)
         k = np.arange(cfg.nfft, dtype=np.float64)
         tw = np.stack([np.cos(2 * np.pi * k / cfg.nfft), -np.sin(2 * np.pi * k / cfg.nfft)], axis=1)
@@ -183,7 +201,7 @@ class Engine:
     def _gemm(self, *, M, N, Cin, x, w, out, taps=((0, 0),), I1=1, I0=None, m1=1, m0=1, J1=1, J0=None,
               xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
               a_stats_stride=0, a_gamma=None, a_beta=None, act=_lib.ACT_NONE, rowbias=None, rowbias_period=0,
-              resid=None, scale=None, addend=None, convt=0, O0=0, stats_out=None, tc=True) -> None:
+              resid=None, scale=None, addend=None, convt=0, O0=0, stats_out=None, stat=(0, 0, 0), tc=True) -> None:
         d = GemmDesc()
         I0 = M if I0 is None else I0
         d.M, d.N, d.K, d.Cin, d.taps = M, N, len(taps) * Cin, Cin, len(taps)
@@ -200,30 +218,29 @@ class Engine:
         d.resid, d.scale, d.addend = ptr(resid), ptr(scale), ptr(addend)
         d.out, d.convt, d.O0 = ptr(out), convt, O0
         d.stats_out = ptr(stats_out)
+        d.stat_div, d.stat_mul, d.stat_mod = stat
         d.math = _lib.MATH_TF32 if (self.mode == "tf32" and tc) else _lib.MATH_FP32
         K = len(taps) * Cin
         rows_in = (M // (I1 * I0)) * d.J1 * d.J0          # input positions (each read once, algorithmically)
         nbytes = 4.0 * (rows_in * Cin + N * K + M * (N if convt else n_out))
         nbytes += 4.0 * M * n_out * ((resid is not None) + (addend is not None))
-        arm = "tc" if d.math == _lib.MATH_TF32 else "simt"
+        arm = "simt"
+        if d.math == _lib.MATH_TF32 and _lib.TEST_HOOK is None:
+            arm = "tc" if _lib.lib().bd_conv_gemm_arm(C.byref(d)) else "simt"
         tile = 128 if N > 64 else 64 if N > 32 else 32 if (N > 16 or act == _lib.ACT_GLU) else 16
         self._k("bd_conv_gemm", C.byref(d), self._stream(), flops=2.0 * M * N * K, nbytes=nbytes,
                 label=f"conv_gemm_{arm}<{tile}>")
 
     # ------------------------------------------------------------------ blocks
-    def _dconv(self, key, prefix: str, x: torch.Tensor, B: int, I1: int, I0: int, C_: int, freq: bool, tag: str):
-        """DConv residual branch in place on x (demucs.py:86-154).  Rows are walked slab-major
-        (b, i1, i0): a slab = one GroupNorm(1) item = (b) in time, (b, fr) in frequency."""
+    def _dconv(self, key, prefix: str, x: torch.Tensor, B: int, T: int, Fr: int, C_: int, tag: str):
+        """DConv residual branch in place on x (demucs.py:86-154); x is [B, T, Fr, C] (Fr = 1 for the
+        time branch).  One GroupNorm(1) item = one (b, fr) row of the reference's [B*Fr, C, T] view
+        (hdemucs.py:146-151); rows are walked in memory order, the slab map picks the item."""
         cfg, W = self.cfg, self.W
         hid = int(C_ / cfg.dconv_comp)
-        M = B * I1 * I0
-        slabs = B * I1
-        if freq:   # x is [B, T(i0), F(i1), C]
-            xs = (I0 * I1 * C_, C_, I1 * C_, 1)
-            us = (I0 * I1 * 2 * C_, 2 * C_, I1 * 2 * C_)
-        else:      # x is [B, T(i0), C], I1 == 1
-            xs = (I0 * C_, 0, C_, 1)
-            us = (I0 * 2 * C_, 0, 2 * C_)
+        M = B * T * Fr
+        slabs = B * Fr
+        stat = (T * Fr, Fr, Fr)                      # slab(m) = b*Fr + fr
         h = self._buf(key, f"dconv_h{tag}", M * hid)
         u = self._buf(key, f"dconv_u{tag}", M * 2 * C_)
         sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64)
@@ -233,17 +250,17 @@ class Engine:
             dil = 2 ** dd
             sums.zero_()
             self._gemm(M=M, N=hid, Cin=C_, x=x, w=W[f"{p}.w1"], bias=W[f"{p}.b1"], out=h,
-                       taps=((0, -dil), (0, 0), (0, dil)), I1=I1, I0=I0, J1=I1, J0=I0, xs=xs,
-                       os_=(I1 * I0 * hid, I0 * hid, hid), stats_out=sums, tc=False)
-            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(I0 * hid), self._stream())
+                       taps=((-dil, 0), (0, 0), (dil, 0)), I1=T, I0=Fr, J1=T, J0=Fr,
+                       xs=(T * Fr * C_, Fr * C_, C_, 1), os_=(T * Fr * hid, Fr * hid, hid),
+                       stats_out=sums, stat=stat, tc=False)
+            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(T * hid), self._stream())
             sums.zero_()
             self._gemm(M=M, N=2 * C_, Cin=hid, x=h, w=W[f"{p}.w2"], bias=W[f"{p}.b2"], out=u,
-                       I1=I1, I0=I0, J1=I1, J0=I0, xs=(I1 * I0 * hid, I0 * hid, hid, 1), os_=us,
                        a_mode=_lib.A_GN_GELU, a_stats=mr, a_gamma=W[f"{p}.g1"], a_beta=W[f"{p}.be1"],
-                       stats_out=sums, tc=False)
-            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(I0 * 2 * C_), self._stream())
+                       stats_out=sums, stat=stat, tc=False)
+            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(T * 2 * C_), self._stream())
             self._k("bd_dconv_tail", ptr(x), ptr(u), ptr(mr), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
-                    ptr(W[f"{p}.scale"]), M, C_, I0 * I1, I1, self._stream(), nbytes=4.0 * M * C_ * 4)
+                    ptr(W[f"{p}.scale"]), M, C_, T * Fr, Fr, self._stream(), nbytes=4.0 * M * C_ * 4)
 
     def _attention_block(self, key, x, kv_src, p: str, attn: str, B: int, Tq: int, Tk: int, tag: str):
         """x += gamma_1 * MHA(q=x_normed, k=v=kv_normed); both inputs are already layer-normed."""
@@ -295,7 +312,7 @@ class Engine:
         sums.zero_()
         self._gemm(M=M, N=D, Cin=Hd, x=hbuf, w=W[f"{p}.linear2.weight"], bias=W[f"{p}.linear2.bias"], out=x,
                    resid=x, scale=W[f"{p}.gamma_2.scale"], I1=1, I0=T, J0=T, xs=(T * Hd, 0, Hd, 1),
-                   os_=(T * D, 0, D), stats_out=sums)
+                   os_=(T * D, 0, D), stats_out=sums, stat=(T, 1, 1))
         self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), B, float(T * D), self._stream())
         self._k("bd_group_norm_apply", ptr(x), ptr(mr), ptr(W[f"{p}.norm_out.weight"]),
                 ptr(W[f"{p}.norm_out.bias"]), B, T, D, self._stream(), nbytes=8.0 * B * T * D)
@@ -359,7 +376,7 @@ class Engine:
                        a_mode=_lib.A_ITEM_AFFINE if first else _lib.A_NONE,
                        a_stats=norm[4:] if first else None, a_stats_stride=8, act=_lib.ACT_GELU)
             if cfg.dconv_mode & 1:
-                self._dconv(key, f"tencoder.{i}", y, B, 1, Tout, Cc, False, "_t")
+                self._dconv(key, f"tencoder.{i}", y, B, Tout, 1, Cc, "_t")
             z = self._buf(key, f"saved_t{i}", B * Tout * Cc)
             self._gemm(M=B * Tout, N=2 * Cc, Cin=Cc, x=y, w=W[f"tencoder.{i}.rewrite.w"],
                        bias=W[f"tencoder.{i}.rewrite.b"], out=z, act=_lib.ACT_GLU)
@@ -376,7 +393,7 @@ class Engine:
                        a_mode=_lib.A_ITEM_AFFINE if first else _lib.A_NONE,
                        a_stats=norm if first else None, a_stats_stride=8, act=_lib.ACT_GELU)
             if cfg.dconv_mode & 1:
-                self._dconv(key, f"encoder.{i}", y, B, Fo, T, Cc, True, "_f")
+                self._dconv(key, f"encoder.{i}", y, B, T, Fo, Cc, "_f")
             z = self._buf(key, f"saved_f{i}", B * T * Fo * Cc)
             emb = W["freq_emb"] if (first and cfg.freq_emb) else None
             self._gemm(M=B * T * Fo, N=2 * Cc, Cin=Cc, x=y, w=W[f"encoder.{i}.rewrite.w"],
@@ -462,13 +479,16 @@ class Engine:
                        bias=W[f"decoder.{j}.rewrite.b"], out=y, taps=taps9, I1=T, I0=Fcur, J1=T, J0=Fcur,
                        xs=(T * Fcur * Cc, Fcur * Cc, Cc, 1), os_=(T * Fcur * Cc, Fcur * Cc, Cc), act=_lib.ACT_GLU)
             if cfg.dconv_mode & 2:
-                self._dconv(key, f"decoder.{j}", y, B, Fcur, T, Cc, True, "_f")
+                self._dconv(key, f"decoder.{j}", y, B, T, Fcur, Cc, "_f")
             # ConvTranspose2d(k=(8,1), s=(4,1)) + crop [2:-2] + GELU (+ next skip) (hdemucs.py:326-334)
             nxt = self._buf(key, names[(j + 1) % 2], dec_f_numel)[: B * T * 4 * Fcur * Cout]
-            self._gemm(M=B * T * (Fcur + 1), N=4 * Cout, Cin=Cc, x=y, w=W[f"decoder.{j}.conv_tr.w"],
-                       bias=W[f"decoder.{j}.conv_tr.b"], out=nxt, taps=((0, 0), (0, -1)), I1=T, I0=Fcur + 1,
-                       J1=T, J0=Fcur, xs=(T * Fcur * Cc, Fcur * Cc, Cc, 1),
-                       os_=(T * 4 * Fcur * Cout, 4 * Fcur * Cout, Cout), convt=1, O0=4 * Fcur,
+            three = self.mode == "tf32" and 4 * Cout >= 64   # tensor-core form: no halo row
+            self._gemm(M=B * T * (Fcur + (0 if three else 1)), N=4 * Cout, Cin=Cc, x=y,
+                       w=W[f"decoder.{j}.conv_tr.w3" if three else f"decoder.{j}.conv_tr.w"],
+                       bias=W[f"decoder.{j}.conv_tr.b"], out=nxt,
+                       taps=((0, -1), (0, 0), (0, 1)) if three else ((0, 0), (0, -1)), I1=T,
+                       I0=Fcur + (0 if three else 1), J1=T, J0=Fcur, xs=(T * Fcur * Cc, Fcur * Cc, Cc, 1),
+                       os_=(T * 4 * Fcur * Cout, 4 * Fcur * Cout, Cout), convt=2 if three else 1, O0=4 * Fcur,
                        act=_lib.ACT_NONE if last else _lib.ACT_GELU, addend=skip)
             if taps is not None:
                 tap(f"dec{j}", (nxt - skip if skip is not None else nxt).view(B, T, 4 * Fcur, Cout), "f")
@@ -481,11 +501,15 @@ class Engine:
                        bias=W[f"tdecoder.{j}.rewrite.b"], out=y, taps=((0, -1), (0, 0), (0, 1)), I1=1, I0=Tin,
                        J1=1, J0=Tin, xs=(Tin * Cc, 0, Cc, 1), os_=(Tin * Cc, 0, Cc), act=_lib.ACT_GLU)
             if cfg.dconv_mode & 2:
-                self._dconv(key, f"tdecoder.{j}", y, B, 1, Tin, Cc, False, "_t")
+                self._dconv(key, f"tdecoder.{j}", y, B, Tin, 1, Cc, "_t")
             nxt = self._buf(key, "dec_tb" if (j % 2 == 0) else "dec_ta", dec_t_numel)[: B * Tout * Cout_t]
-            self._gemm(M=B * (Tin + 1), N=4 * Cout_t, Cin=Cc, x=y, w=W[f"tdecoder.{j}.conv_tr.w"],
-                       bias=W[f"tdecoder.{j}.conv_tr.b"], out=nxt, taps=((0, 0), (0, -1)), I1=1, I0=Tin + 1,
-                       J1=1, J0=Tin, xs=(Tin * Cc, 0, Cc, 1), os_=(Tout * Cout_t, 0, Cout_t), convt=1, O0=Tout,
+            three = self.mode == "tf32" and 4 * Cout_t >= 64
+            self._gemm(M=B * (Tin + (0 if three else 1)), N=4 * Cout_t, Cin=Cc, x=y,
+                       w=W[f"tdecoder.{j}.conv_tr.w3" if three else f"tdecoder.{j}.conv_tr.w"],
+                       bias=W[f"tdecoder.{j}.conv_tr.b"], out=nxt,
+                       taps=((0, -1), (0, 0), (0, 1)) if three else ((0, 0), (0, -1)), I1=1,
+                       I0=Tin + (0 if three else 1), J1=1, J0=Tin, xs=(Tin * Cc, 0, Cc, 1),
+                       os_=(Tout * Cout_t, 0, Cout_t), convt=2 if three else 1, O0=Tout,
                        act=_lib.ACT_NONE if last else _lib.ACT_GELU, addend=skip_t)
             if taps is not None:
                 tap(f"tdec{j}", (nxt - skip_t if skip_t is not None else nxt).view(B, Tout, Cout_t), "t")

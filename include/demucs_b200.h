@@ -51,7 +51,7 @@ typedef struct bd_gemm_desc {
   const float* bias;   /* [N] or NULL */
   /* A prologue */
   int a_mode;
-  const float* a_stats; /* GN_GELU: [slab][2] = mean, rstd, slab = m / I0.  ITEM_AFFINE: per item b,
+  const float* a_stats; /* GN_GELU: [slab][2] = mean, rstd, slab(m) as below.  ITEM_AFFINE: per item b,
                            a_stats[b*a_stats_stride + 0] = mean, [+2] = 1/(eps+std) */
   int a_stats_stride;
   const float* a_gamma; /* [Cin] (GN_GELU) */
@@ -66,9 +66,16 @@ typedef struct bd_gemm_desc {
   const float* addend;
   float* out;          /* out index = b*os_b + i1*os_1 + o0*os_0 + n_out */
   long long os_b, os_1, os_0;
-  int convt;           /* 1: N = 4*Cout, r = n / Cout, o0 = 4*i0 + r - 2 (cropped transposed conv), else o0 = i0 */
+  int convt;           /* 0: o0 = i0.  Transposed conv k=8,s=4 with N = 4*Cout, r = n / Cout:
+                          1: rows = input positions + 1, taps (0,-1): o0 = 4*i0 + r - 2
+                          2: rows = input positions, taps (-1,0,+1), zero-extended weights: o0 = 4*i0 + r */
   int O0;              /* convt: valid output positions are 0 <= o0 < O0 */
-  double* stats_out;   /* [slab][2] += (sum, sumsq) of stored values, slab = m / I0; or NULL */
+  double* stats_out;   /* [slab][2] += (sum, sumsq) of stored values; or NULL */
+  /* GroupNorm slab of row m (for stats_out and for the GN_GELU prologue):
+   *   slab(m) = (m / stat_div) * stat_mul + (m % stat_mod)
+   * time branch / tokens: one slab per item (stat_div = rows per item, stat_mul = stat_mod = 1);
+   * frequency branch [B,T,F,C]: one slab per (b, fr): stat_div = T*F, stat_mul = stat_mod = F. */
+  int stat_div, stat_mul, stat_mod;
   int math;            /* BD_MATH_* */
 } bd_gemm_desc;
 
@@ -90,6 +97,8 @@ int bd_ola_combine(const float* frames, const float* xt, const float* norm, floa
 
 /* K3/K4/K7: implicit-GEMM convolution / linear layer, see bd_gemm_desc. */
 int bd_conv_gemm(const bd_gemm_desc* desc, void* stream);
+/* Which arm bd_conv_gemm will use for this descriptor: 0 = fp32 CUDA-core, 1 = tcgen05 TF32. */
+int bd_conv_gemm_arm(const bd_gemm_desc* desc);
 
 /* K5 (GroupNorm(1,C) demucs.py:123, MyGroupNorm transformer.py:258-268): (sum,sumsq) -> (mean, rstd),
  * biased variance, eps 1e-5.  count = elements per slab. */

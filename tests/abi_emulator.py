@@ -105,7 +105,8 @@ def bd_conv_gemm(dref, stream):
             x = f32(d.x, int(idx.max()) + 1)
             vals = x[idx]
             if d.a_mode == _lib.A_GN_GELU:
-                st = f32(d.a_stats, 2 * (M // d.I0)).reshape(-1, 2)[(m // d.I0)[ok]]
+                sl = (m // d.stat_div) * d.stat_mul + (m % d.stat_mod)
+                st = f32(d.a_stats, 2 * (int(sl.max()) + 1)).reshape(-1, 2)[sl[ok]]
                 g, be = f32(d.a_gamma, Cin), f32(d.a_beta, Cin)
                 vals = gelu((vals - st[:, :1]) * st[:, 1:2] * g + be)
             elif d.a_mode == _lib.A_ITEM_AFFINE:
@@ -125,7 +126,7 @@ def bd_conv_gemm(dref, stream):
     if d.convt:
         cout = N // 4
         r, co = n // cout, n % cout
-        o0 = 4 * i0[:, None] + r[None, :] - 2
+        o0 = 4 * i0[:, None] + r[None, :] - (2 if d.convt == 1 else 0)
         ok = (o0 >= 0) & (o0 < d.O0)
         oidx = (b * d.os_b + i1 * d.os_1)[:, None] + o0 * d.os_0 + co[None, :]
     else:
@@ -143,11 +144,12 @@ def bd_conv_gemm(dref, stream):
     v = v.astype(np.float32)
     f32(d.out, nmax)[oidx[ok]] = v[ok]
     if d.stats_out:
-        slabs = M // d.I0
+        sl = (m // d.stat_div) * d.stat_mul + (m % d.stat_mod)
+        slabs = int(sl.max()) + 1
         st = f64(d.stats_out, 2 * slabs).reshape(slabs, 2)
         v64 = np.where(ok, v, 0).astype(np.float64)
-        np.add.at(st[:, 0], m // d.I0, v64.sum(1))
-        np.add.at(st[:, 1], m // d.I0, (v64 ** 2).sum(1))
+        np.add.at(st[:, 0], sl, v64.sum(1))
+        np.add.at(st[:, 1], sl, (v64 ** 2).sum(1))
 
 
 def bd_finalize_group_stats(sums, mean_rstd, slabs, count, stream):

@@ -36,6 +36,7 @@ def run_plain(M, N, K, math_mode, bias=True, act=_lib.ACT_NONE, resid=False, sta
     d.x, d.w, d.bias, d.out = ptr(xfull), ptr(w), ptr(b), ptr(out)
     d.act, d.resid, d.scale = act, ptr(r), ptr(sc)
     d.stats_out = ptr(sums) if stats_rows else None
+    d.stat_div, d.stat_mul, d.stat_mod = (stats_rows or M), 1, 1
     d.math = math_mode
     _lib.call("bd_conv_gemm", C.byref(d), 0)
     torch.cuda.synchronize()

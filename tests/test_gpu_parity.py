@@ -228,3 +228,21 @@ def test_forward_htdemucs_tf32_mode(name):
     stems = stem_errors(got.cpu(), want)
     print("per-stem", stems)
     assert max(stems) < STEM_TOL
+
+
+def test_forward_blocks_small_tf32_mode():
+    """Small geometry through the tensor-core arm (16/32-float k-blocks, R0 < 128 tiles, 3-tap transposed
+    convs): every block within TF32 rounding of the fp32 oracle."""
+    g = golden("small_ls05.npz")
+    cfg = small_config()
+    W, mix = forward_fixture_inputs(g, cfg)
+    taps_o, taps = {}, {}
+    with torch.no_grad():
+        want = htdemucs_forward(W, cfg, mix, taps_o)
+    eng = Engine(cfg, W, DEV, mode="tf32")
+    got = eng.forward(mix.to(DEV), taps)
+    torch.cuda.synchronize()
+    errs = {k: rel_l2(taps[k].cpu(), v) for k, v in taps_o.items()}
+    print("small tf32 taps", {k: f"{e:.1e}" for k, e in errs.items()})
+    assert max(errs.values()) < 3e-3
+    assert max(stem_errors(got.cpu(), want)) < 1e-3
