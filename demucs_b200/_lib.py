@@ -40,6 +40,7 @@ class GemmDesc(C.Structure):
         ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
         ("a_mode", C.c_int), ("a_stats", C.c_void_p), ("a_stats_stride", C.c_int),
         ("a_gamma", C.c_void_p), ("a_beta", C.c_void_p),
+        ("e_stats", C.c_void_p), ("e_gamma", C.c_void_p), ("e_beta", C.c_void_p),
         ("act", C.c_int), ("rowbias", C.c_void_p), ("rowbias_period", C.c_int),
         ("resid", C.c_void_p), ("scale", C.c_void_p), ("addend", C.c_void_p),
         ("out", C.c_void_p), ("os_b", C.c_longlong), ("os_1", C.c_longlong), ("os_0", C.c_longlong),

@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
   // otherwise (frequency branch, slab = (b, fr) changes with every row) each row reduces across the TX
   // threads that share it and issues its own pair of atomics.
   const bool row_stats = d.stats_out && d.stat_mod != 1;
+  const bool vec = bd_epi_vec_ok(d);
   double ssum = 0.0, ssq = 0.0;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -240,14 +241,23 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
     float rs = 0.f, rq = 0.f;
     if (ok) {
       const EpiRow er = bd_epi_row(d, m);
+      if (TN >= 4 && vec) {
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int n = n0 + col_of(j);
-        if (n >= d.N) continue;
-        float v;
-        if (bd_epi_apply(d, er, n, acc[i][j], acc[i][(j + 1) % TN], v)) {
-          rs += v;
-          rq = fmaf(v, v, rq);
+        for (int j = 0; j < TN; j += 4) {
+          const int n = n0 + col_of(j);
+          if (n < d.N) bd_epi_apply4(d, er, n, make_float4(acc[i][j], acc[i][(j + 1) % TN], acc[i][(j + 2) % TN],
+                                                           acc[i][(j + 3) % TN]), rs, rq);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int n = n0 + col_of(j);
+          if (n >= d.N) continue;
+          float v;
+          if (bd_epi_apply(d, er, n, acc[i][j], acc[i][(j + 1) % TN], v)) {
+            rs += v;
+            rq = fmaf(v, v, rq);
+          }
         }
       }
     }
@@ -297,7 +307,8 @@ int bd_conv_gemm_simt(const bd_gemm_desc* dp, void* stream) {
   BD_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "bd_conv_gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
   BD_REQUIRE(d.taps >= 1 && d.taps <= BD_MAX_TAPS && d.K == d.taps * d.Cin, "bd_conv_gemm: K != taps*Cin");
   BD_REQUIRE(d.I0 > 0 && d.I1 > 0 && d.M % ((long long)d.I0 * d.I1) == 0, "bd_conv_gemm: M not a multiple of I1*I0");
-  BD_REQUIRE(d.x && d.w && d.out, "bd_conv_gemm: null tensor");
+  BD_REQUIRE(d.x && d.w && (d.out || d.stats_out), "bd_conv_gemm: null tensor");
+  BD_REQUIRE(!d.e_stats || (d.e_gamma && d.e_beta && d.stat_div > 0), "bd_conv_gemm: epilogue GroupNorm needs affine + slab map");
   BD_REQUIRE(d.act != BD_ACT_GLU || (d.N % 2 == 0 && !d.convt), "bd_conv_gemm: GLU needs even N and no convt");
   BD_REQUIRE(!d.convt || d.N % 4 == 0, "bd_conv_gemm: convt needs N = 4*Cout");
   BD_REQUIRE(d.a_mode == BD_A_NONE || d.a_stats, "bd_conv_gemm: a_mode without a_stats");

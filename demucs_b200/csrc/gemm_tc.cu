@@ -226,19 +226,30 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     EpiRow er;
     if (row_ok) er = bd_epi_row(d, m);
     float ssum = 0.f, ssq = 0.f;
+    const bool vec = bd_epi_vec_ok(d);
     for (int c0 = 0; c0 < TBN; c0 += 32) {
       if (n0 + c0 >= d.N) break;            // warp-uniform
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
       if (row_ok) {
+        if (vec) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < d.N) {
-            float st;
-            if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) & 31]), st)) {
-              ssum += st;
-              ssq = fmaf(st, st, ssq);
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            if (n < d.N)
+              bd_epi_apply4(d, er, n, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), ssum, ssq);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < d.N) {
+              float st;
+              if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) & 31]), st)) {
+                ssum += st;
+                ssq = fmaf(st, st, ssq);
+              }
             }
           }
         }

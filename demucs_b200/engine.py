@@ -185,7 +185,8 @@ class Engine:
             pool[name] = t
         return t[:numel]
 
-    def _k(self, name: str, *args, flops: float = 0.0, nbytes: float = 0.0, label: tp.Optional[str] = None) -> None:
+    def _k(self, name: str, *args, flops: float = 0.0, nbytes: float = 0.0, label: tp.Optional[str] = None,
+           detail: str = "") -> None:
         """Launch one kernel through the C ABI.  ``flops`` / ``nbytes`` are the ALGORITHMIC work of the
         launch, recorded with CUDA events when a profile is being taken."""
         self.launches += 1
@@ -196,12 +197,13 @@ class Engine:
         e0.record()
         _lib.call(name, *args)
         e1.record()
-        self._prof.append((label or name, e0, e1, flops, nbytes))
+        self._prof.append((label or name, e0, e1, flops, nbytes, detail))
 
     def _gemm(self, *, M, N, Cin, x, w, out, taps=((0, 0),), I1=1, I0=None, m1=1, m0=1, J1=1, J0=None,
               xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
               a_stats_stride=0, a_gamma=None, a_beta=None, act=_lib.ACT_NONE, rowbias=None, rowbias_period=0,
-              resid=None, scale=None, addend=None, convt=0, O0=0, stats_out=None, stat=(0, 0, 0), tc=True) -> None:
+              resid=None, scale=None, addend=None, convt=0, O0=0, stats_out=None, stat=(0, 0, 0),
+              e_stats=None, e_gamma=None, e_beta=None, tc=True) -> None:
         d = GemmDesc()
         I0 = M if I0 is None else I0
         d.M, d.N, d.K, d.Cin, d.taps = M, N, len(taps) * Cin, Cin, len(taps)
@@ -214,6 +216,7 @@ class Engine:
         d.x, d.w, d.bias = ptr(x), ptr(w), ptr(bias)
         d.a_mode, d.a_stats, d.a_stats_stride = a_mode, ptr(a_stats), a_stats_stride
         d.a_gamma, d.a_beta = ptr(a_gamma), ptr(a_beta)
+        d.e_stats, d.e_gamma, d.e_beta = ptr(e_stats), ptr(e_gamma), ptr(e_beta)
         d.act, d.rowbias, d.rowbias_period = act, ptr(rowbias), rowbias_period
         d.resid, d.scale, d.addend = ptr(resid), ptr(scale), ptr(addend)
         d.out, d.convt, d.O0 = ptr(out), convt, O0
@@ -222,14 +225,15 @@ class Engine:
         d.math = _lib.MATH_TF32 if (self.mode == "tf32" and tc) else _lib.MATH_FP32
         K = len(taps) * Cin
         rows_in = (M // (I1 * I0)) * d.J1 * d.J0          # input positions (each read once, algorithmically)
-        nbytes = 4.0 * (rows_in * Cin + N * K + M * (N if convt else n_out))
+        nbytes = 4.0 * (rows_in * Cin + N * K + (M * (N if convt else n_out) if out is not None else 0))
         nbytes += 4.0 * M * n_out * ((resid is not None) + (addend is not None))
         arm = "simt"
         if d.math == _lib.MATH_TF32 and _lib.TEST_HOOK is None:
             arm = "tc" if _lib.lib().bd_conv_gemm_arm(C.byref(d)) else "simt"
         tile = 128 if N > 64 else 64 if N > 32 else 32 if (N > 16 or act == _lib.ACT_GLU) else 16
         self._k("bd_conv_gemm", C.byref(d), self._stream(), flops=2.0 * M * N * K, nbytes=nbytes,
-                label=f"conv_gemm_{arm}<{tile}>")
+                label=f"conv_gemm_{arm}<{tile}>",
+                detail=f"M={M} N={N} K={K} taps={len(taps)} act={act} a={a_mode} stats={int(stats_out is not None)}")
 
     # ------------------------------------------------------------------ blocks
     def _dconv(self, key, prefix: str, x: torch.Tensor, B: int, T: int, Fr: int, C_: int, tag: str):
@@ -242,25 +246,30 @@ class Engine:
         slabs = B * Fr
         stat = (T * Fr, Fr, Fr)                      # slab(m) = b*Fr + fr
         h = self._buf(key, f"dconv_h{tag}", M * hid)
-        u = self._buf(key, f"dconv_u{tag}", M * 2 * C_)
         sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64)
-        mr = self._buf(key, f"dconv_mr{tag}", 2 * slabs)
+        mr1 = self._buf(key, f"dconv_mr1{tag}", 2 * slabs)
+        mr2 = self._buf(key, f"dconv_mr2{tag}", 2 * slabs)
         for dd in range(cfg.dconv_depth):
             p = f"{prefix}.dconv.layers.{dd}"
             dil = 2 ** dd
+            # (1) h = conv3_dilated(x) and the GroupNorm statistics of h
             sums.zero_()
             self._gemm(M=M, N=hid, Cin=C_, x=x, w=W[f"{p}.w1"], bias=W[f"{p}.b1"], out=h,
                        taps=((-dil, 0), (0, 0), (dil, 0)), I1=T, I0=Fr, J1=T, J0=Fr,
                        xs=(T * Fr * C_, Fr * C_, C_, 1), os_=(T * Fr * hid, Fr * hid, hid),
                        stats_out=sums, stat=stat, tc=False)
-            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(T * hid), self._stream())
+            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr1), slabs, float(T * hid), self._stream())
+            # (2) statistics of u = conv1x1(gelu(gn(h))) WITHOUT storing u: the expanded [.., 2C] tensor
+            #     never touches HBM, it is recomputed from the 8x narrower h in (3)
             sums.zero_()
-            self._gemm(M=M, N=2 * C_, Cin=hid, x=h, w=W[f"{p}.w2"], bias=W[f"{p}.b2"], out=u,
-                       a_mode=_lib.A_GN_GELU, a_stats=mr, a_gamma=W[f"{p}.g1"], a_beta=W[f"{p}.be1"],
-                       stats_out=sums, stat=stat, tc=False)
-            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), slabs, float(T * 2 * C_), self._stream())
-            self._k("bd_dconv_tail", ptr(x), ptr(u), ptr(mr), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
-                    ptr(W[f"{p}.scale"]), M, C_, T * Fr, Fr, self._stream(), nbytes=4.0 * M * C_ * 4)
+            common = dict(M=M, N=2 * C_, Cin=hid, x=h, w=W[f"{p}.w2"], bias=W[f"{p}.b2"],
+                          a_mode=_lib.A_GN_GELU, a_stats=mr1, a_gamma=W[f"{p}.g1"], a_beta=W[f"{p}.be1"],
+                          stat=stat, tc=False)
+            self._gemm(out=None, stats_out=sums, **common)
+            self._k("bd_finalize_group_stats", ptr(sums), ptr(mr2), slabs, float(T * 2 * C_), self._stream())
+            # (3) x += scale * GLU(gn(u)), in place
+            self._gemm(out=x, e_stats=mr2, e_gamma=W[f"{p}.g2"], e_beta=W[f"{p}.be2"], act=_lib.ACT_GLU,
+                       resid=x, scale=W[f"{p}.scale"], **common)
 
     def _attention_block(self, key, x, kv_src, p: str, attn: str, B: int, Tq: int, Tk: int, tag: str):
         """x += gamma_1 * MHA(q=x_normed, k=v=kv_normed); both inputs are already layer-normed."""

@@ -56,8 +56,12 @@ typedef struct bd_gemm_desc {
   int a_stats_stride;
   const float* a_gamma; /* [Cin] (GN_GELU) */
   const float* a_beta;  /* [Cin] */
-  /* epilogue, in this order: v = acc + bias; v = act(v); v += rowbias[(m % period)*Nout + n];
-   * v = resid + scale[n]*v (scale NULL -> 1); v += addend; store; accumulate stats of stored v */
+  /* epilogue, in this order: v = acc + bias; [GroupNorm: v = (v - mean)*rstd*e_gamma[n] + e_beta[n]];
+   * v = act(v); v += rowbias[(m % period)*Nout + n]; v = resid + scale[n]*v (scale NULL -> 1);
+   * v += addend; store (skipped when out is NULL: statistics-only pass); accumulate stats of v */
+  const float* e_stats;  /* [slab][2] = mean, rstd of THIS layer's pre-activation output (slab map below), or NULL */
+  const float* e_gamma;  /* [N] */
+  const float* e_beta;   /* [N] */
   int act;
   const float* rowbias;
   int rowbias_period;

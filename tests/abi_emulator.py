@@ -117,6 +117,10 @@ def bd_conv_gemm(dref, stream):
     v = A @ w.T
     if d.bias:
         v = v + f32(d.bias, N)
+    if d.e_stats:
+        sl = (m // d.stat_div) * d.stat_mul + (m % d.stat_mod)
+        st = f32(d.e_stats, 2 * (int(sl.max()) + 1)).reshape(-1, 2)[sl]
+        v = (v - st[:, :1]) * st[:, 1:2] * f32(d.e_gamma, N) + f32(d.e_beta, N)
     if d.act == _lib.ACT_GELU:
         v = gelu(v)
     elif d.act == _lib.ACT_GLU:
@@ -142,7 +146,8 @@ def bd_conv_gemm(dref, stream):
     if d.addend:
         v = v + np.where(ok, f32(d.addend, nmax)[np.where(ok, oidx, 0)], 0)
     v = v.astype(np.float32)
-    f32(d.out, nmax)[oidx[ok]] = v[ok]
+    if d.out:
+        f32(d.out, nmax)[oidx[ok]] = v[ok]
     if d.stats_out:
         sl = (m // d.stat_div) * d.stat_mul + (m % d.stat_mod)
         slabs = int(sl.max()) + 1

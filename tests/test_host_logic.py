@@ -1,0 +1,91 @@
+"""CPU: the product's host logic (weight packing, implicit-GEMM descriptors, buffer plumbing, the
+apply_model batcher, BagOfModels, Separator) checked against the oracle / reference goldens with the
+numpy ABI emulator standing in for the CUDA library (tests/abi_emulator.py)."""
+import random
+
+import pytest
+import torch
+
+from abi_emulator import emulated_abi, CALLS
+from oracle.htdemucs_oracle import htdemucs_forward
+from _fixtures import (golden, rel_l2, strided, small_config, synth_mix, init_weights, forward_fixture_inputs,
+                       APPLY_CASES, BAG_WEIGHTS)
+import demucs_b200 as D
+from demucs_b200.engine import Engine
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_engine_forward_matches_oracle_and_golden(mode):
+    """Both descriptor forms (the tf32 mode uses the 3-tap transposed-conv packing)."""
+    g = golden("small_short.npz")
+    cfg = small_config()
+    W, mix = forward_fixture_inputs(g, cfg)
+    taps_o, taps = {}, {}
+    with torch.no_grad():
+        want = htdemucs_forward(W, cfg, mix, taps_o)
+    with emulated_abi():
+        eng = Engine(cfg, W, "cpu", mode=mode)
+        got = eng.forward(mix, taps if mode == "fp32" else None)
+    assert rel_l2(got, want) < 1e-5
+    assert rel_l2(strided(got, int(g["stride"])), g["out"]) < 1e-5
+    for k, v in taps.items():
+        ref = taps_o[k][..., :v.shape[-1]] if k in ("istft", "time_out") else taps_o[k]
+        assert rel_l2(v, ref) < 1e-5, k
+
+
+def test_apply_model_and_bag_match_reference_golden():
+    g = golden("apply_small.npz")
+    cfg = small_config()
+    models = [D.HTDemucs.from_config(cfg, init_seed=s, layer_scale=0.5) for s in range(2)]
+    mix = synth_mix(1, int(g["length"]), 99)
+    stride = int(g["stride"])
+    with emulated_abi():
+        for name in ("power2", "nosplit"):   # shifts + RNG stream + transition power; leaf branch
+            m = mix[..., :50000] if name == "nosplit" else mix
+            random.seed(0)
+            out = D.apply_model(models[0], m.clone(), **APPLY_CASES[name])
+            assert rel_l2(strided(out, stride), g[name]) < 1e-5, name
+        random.seed(0)
+        out = D.apply_model(D.BagOfModels(models, BAG_WEIGHTS), mix.clone(), shifts=1)
+        assert rel_l2(strided(out, stride), g["bag"]) < 1e-5
+
+
+def test_callbacks_and_errors():
+    cfg = small_config()
+    model = D.HTDemucs.from_config(cfg, init_seed=0)
+    mix = synth_mix(1, 90000, 1)
+    events = []
+    with emulated_abi():
+        D.apply_model(model, mix, shifts=0, callback=events.append, callback_arg={"tag": 7})
+        with pytest.raises(ValueError):
+            model(torch.zeros(1, 2, cfg.segment_length + 1))
+        with pytest.raises(AssertionError):
+            D.apply_model(model, mix, transition_power=0.5)
+
+        def boom(d):
+            raise KeyboardInterrupt
+        with pytest.raises(KeyboardInterrupt):
+            D.apply_model(model, mix, shifts=0, callback=boom)
+    # reference callback contract (api.py:108-115): start/end per segment, with the progress keys
+    assert [e["state"] for e in events] == ["start", "start", "end", "end"]
+    assert {e["segment_offset"] for e in events} == {0, int(0.75 * cfg.segment_length)}
+    assert all(e["tag"] == 7 and e["models"] == 1 and e["shift_idx"] == 0 for e in events)
+    with pytest.raises(NotImplementedError):
+        D.BagOfModels([model]).forward(mix)
+    with pytest.raises(D.UnsupportedConfig):
+        D.HTDemucs(["a"], cac=False)
+    with pytest.raises(D.KernelError):                    # no CPU / PyTorch fallback outside the emulator
+        model(torch.zeros(1, 2, 4096))
+
+
+def test_tensor_chunk_and_center_trim_follow_reference_semantics():
+    x = torch.arange(20.).view(1, 1, 20)
+    c = D.TensorChunk(x, 5, 6)
+    assert c.shape == [1, 1, 6]
+    assert c.padded(10)[0, 0].tolist() == list(range(3, 13))          # real neighbours, not zeros
+    assert D.TensorChunk(x, 16, 10).padded(8)[0, 0].tolist() == [14., 15., 16., 17., 18., 19., 0., 0.]
+    nested = D.TensorChunk(c, 2, 100)
+    assert (nested.offset, nested.length) == (7, 4)
+    assert D.center_trim(x, 15)[0, 0].tolist() == list(range(2, 17))  # odd surplus trimmed on the right
+    with pytest.raises(ValueError):
+        D.center_trim(x, 21)
