@@ -31,15 +31,18 @@
 
 namespace {
 
-constexpr int TBM = 128, TBN = 128;                // tile rows / columns
-constexpr int kTmemCols = 128;
+constexpr int TBM = 128;                           // tile rows (UMMA M)
 constexpr int kThreads = 192;
 
-template <int TBK>
-struct Cfg {                                       // TBK floats per k-block: 32 -> 128B swizzle, 16 -> 64B swizzle
-  static constexpr int kStages = TBK == 32 ? 3 : 6;
+// TBK floats per k-block: 32 -> 128B swizzle, 16 -> 64B swizzle.  TBN = tile columns = UMMA N (16..128):
+// narrow outputs (DConv hidden widths, last-layer channels) get narrow tiles instead of zero padding.
+template <int TBK, int TBN>
+struct Cfg {
   static constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
+  static constexpr int kStagesRaw = 98304 / (kStageBytesA + kStageBytesB);   // ~96 KB: two CTAs per SM
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = TBN < 32 ? 32 : TBN;
 };
 
 struct TileGeom {
@@ -133,13 +136,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ---- kernel -------------------------------------------------------------------------------------------
-template <int TBK>
+template <int TBK, int TBN>
 __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const bd_gemm_desc d, const TileGeom g) {
-  using C_ = Cfg<TBK>;
+  using C_ = Cfg<TBK, TBN>;
   constexpr int kStages = C_::kStages, kStageBytesA = C_::kStageBytesA, kStageBytesB = C_::kStageBytesB;
+  constexpr int kTmemCols = C_::kTmemCols;
+  constexpr int CW = TBN < 32 ? TBN : 32;            // columns per TMEM load
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -227,14 +242,15 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     if (row_ok) er = bd_epi_row(d, m);
     float ssum = 0.f, ssq = 0.f;
     const bool vec = bd_epi_vec_ok(d);
-    for (int c0 = 0; c0 < TBN; c0 += 32) {
+    for (int c0 = 0; c0 < TBN; c0 += CW) {
       if (n0 + c0 >= d.N) break;            // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      uint32_t v[CW];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
       if (row_ok) {
         if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < CW; j += 4) {
             const int n = n0 + c0 + j;
             if (n < d.N)
               bd_epi_apply4(d, er, n, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
@@ -242,11 +258,11 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CW; ++j) {
             const int n = n0 + c0 + j;
             if (n < d.N) {
               float st;
-              if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) & 31]), st)) {
+              if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) % CW]), st)) {
                 ssum += st;
                 ssq = fmaf(st, st, ssq);
               }
@@ -256,16 +272,24 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
       }
     }
     if (d.stats_out) {
-      double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
-      if (lane == 0) {
-        red[quarter] = ds;
-        red[4 + quarter] = dq;
+      if (d.stat_mod != 1) {                // frequency branch: the GroupNorm slab changes with every row
+        if (row_ok) {
+          const int sl = bd_stat_slab(d, m);
+          atomicAdd(&d.stats_out[2 * (size_t)sl], (double)ssum);
+          atomicAdd(&d.stats_out[2 * (size_t)sl + 1], (double)ssq);
+        }
+      } else {
+        double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
+        if (lane == 0) {
+          red[quarter] = ds;
+          red[4 + quarter] = dq;
+        }
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (d.stats_out && threadIdx.x == 0) {   // host guarantees one slab per tile (I1 == 1, I0 == stat_div)
+  if (d.stats_out && d.stat_mod == 1 && threadIdx.x == 0) {   // host guarantees one slab per tile
     const int sl = bd_stat_slab(d, (long long)b * d.I1 * d.I0 + i0s);
     atomicAdd(&d.stats_out[2 * (size_t)sl], red[0] + red[1] + red[2] + red[3]);
     atomicAdd(&d.stats_out[2 * (size_t)sl + 1], red[4] + red[5] + red[6] + red[7]);
@@ -310,9 +334,9 @@ int pow2_ceil(int v) {
   return p;
 }
 
-template <int TBK>
+template <int TBK, int TBN>
 int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st) {
-  using C_ = Cfg<TBK>;
+  using C_ = Cfg<TBK, TBN>;
   alignas(64) CUtensorMap map_a, map_b;
   // activations: (c, j0, j1, item); size-1 axes get a harmless contiguous stride
   const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
@@ -321,7 +345,7 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
   cuuint32_t abox[4] = {(cuuint32_t)TBK, (cuuint32_t)g.R0, (cuuint32_t)g.R1, 1};
   cuuint64_t bdim[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
   cuuint64_t bstr[1] = {(cuuint64_t)d.K * 4};
-  cuuint32_t bbox[2] = {(cuuint32_t)TBK, (cuuint32_t)TBN};
+  cuuint32_t bbox[2] = {(cuuint32_t)TBK, (cuuint32_t)TBN};   // weight rows past N are zero-filled
   if (!encode(&map_a, d.x, 4, adim, astr, abox, TBK) || !encode(&map_b, d.w, 2, bdim, bstr, bbox, TBK)) {
     bd_set_error("bd_conv_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d Cin=%d J0=%d J1=%d)", d.M, d.N, d.K,
                  d.Cin, d.J0, d.J1);
@@ -329,7 +353,7 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<TBK, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C_::kSmemBytes);
     if (e != cudaSuccess) {
       bd_set_error("bd_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -338,7 +362,7 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
     configured = true;
   }
   dim3 grid((unsigned)((long long)items * g.blocks1 * g.blocks0), (d.N + TBN - 1) / TBN);
-  conv_gemm_tc_kernel<TBK><<<grid, kThreads, C_::kSmemBytes, st>>>(map_a, map_b, d, g);
+  conv_gemm_tc_kernel<TBK, TBN><<<grid, kThreads, C_::kSmemBytes, st>>>(map_a, map_b, d, g);
   return bd_check_launch("conv_gemm_tc_kernel");
 }
 
@@ -347,10 +371,10 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
 // eligibility: unit-stride implicit GEMM, channels-last, big enough to fill tensor-core tiles
 bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d) {
   if (d.a_mode != BD_A_NONE || d.xs_c != 1 || d.m0 != 1 || d.m1 != 1) return false;
-  if (d.Cin % 16 != 0 || d.N < 64 || d.K < 32 || d.M < 128 || d.taps > BD_MAX_TAPS) return false;
+  if (d.Cin % 16 != 0 || d.N < 16 || d.K < 16 || d.M < 128 || d.taps > BD_MAX_TAPS) return false;
   if (d.xs_0 % 4 != 0 || (d.J1 > 1 && d.xs_1 % 4 != 0) || d.xs_b % 4 != 0) return false;
   if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15)) return false;
-  if (d.stats_out && !(d.stat_mod == 1 && d.I1 == 1 && d.I0 == d.stat_div)) return false;
+  if (d.stats_out && d.stat_mod == 1 && !(d.I1 == 1 && d.I0 == d.stat_div)) return false;
   return true;
 }
 
@@ -369,13 +393,18 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   g.blocks1 = (d.I1 + g.R1 - 1) / g.R1;
   const int items = d.M / (d.I0 * d.I1);
   int rc;
+  const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
+  const cudaStream_t st = (cudaStream_t)stream;
+#define BD_TC_CASE(K_, N_) \
+  if (tbn == N_) rc = launch_tc<K_, N_>(d, g, items, st); else
   if (d.Cin % 32 == 0) {
     g.cpb = d.Cin / 32;
-    rc = launch_tc<32>(d, g, items, (cudaStream_t)stream);
+    BD_TC_CASE(32, 16) BD_TC_CASE(32, 32) BD_TC_CASE(32, 64) rc = launch_tc<32, 128>(d, g, items, st);
   } else {
     g.cpb = d.Cin / 16;
-    rc = launch_tc<16>(d, g, items, (cudaStream_t)stream);
+    BD_TC_CASE(16, 16) BD_TC_CASE(16, 32) BD_TC_CASE(16, 64) rc = launch_tc<16, 128>(d, g, items, st);
   }
+#undef BD_TC_CASE
   *handled = 1;
   return rc;
 }

@@ -47,6 +47,27 @@ __global__ void dconv_tail_kernel(float* __restrict__ x, const float* __restrict
   *xp = xv;
 }
 
+// h[m, c] = gelu(gn(h[m, c])) in place; one thread = one float4
+__global__ void gn_gelu_apply_kernel(float* __restrict__ h, const float* __restrict__ mr,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, long long total4,
+                                     int C4, long long rows_per_item, int slabs_per_item) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const long long m = i / C4;
+  const int c4 = (int)(i - m * C4);
+  const long long slab = (m / rows_per_item) * slabs_per_item + (m % slabs_per_item);
+  const float mean = __ldg(mr + 2 * slab), rstd = __ldg(mr + 2 * slab + 1);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+  float4* p = reinterpret_cast<float4*>(h) + i;
+  float4 v = *p;
+  v.x = bd_gelu(fmaf((v.x - mean) * rstd, g.x, b.x));
+  v.y = bd_gelu(fmaf((v.y - mean) * rstd, g.y, b.y));
+  v.z = bd_gelu(fmaf((v.z - mean) * rstd, g.z, b.z));
+  v.w = bd_gelu(fmaf((v.w - mean) * rstd, g.w, b.w));
+  *p = v;
+}
+
 // One warp per row.  C <= 1024, C % 4 == 0.
 template <int MAXV>
 __global__ void layer_norm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
@@ -156,6 +177,15 @@ int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float*
   dconv_tail_kernel<<<bd_cdiv(total2, 256), 256, 0, (cudaStream_t)stream>>>(x, u, mean_rstd, gamma, beta, scale, total2,
                                                                            C, rows_per_item, slabs_per_item);
   return bd_check_launch("dconv_tail_kernel");
+}
+
+int bd_gn_gelu_apply(float* h, const float* mean_rstd, const float* gamma, const float* beta, long long M, int C,
+                     long long rows_per_item, int slabs_per_item, void* stream) {
+  BD_REQUIRE(C % 4 == 0 && M > 0 && rows_per_item > 0 && slabs_per_item > 0, "bd_gn_gelu_apply: bad sizes (C=%d)", C);
+  long long total4 = M * (C / 4);
+  gn_gelu_apply_kernel<<<bd_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(h, mean_rstd, gamma, beta, total4, C / 4,
+                                                                              rows_per_item, slabs_per_item);
+  return bd_check_launch("gn_gelu_apply_kernel");
 }
 
 int bd_layer_norm(const float* x, float* y, const float* gamma, const float* beta, const float* pos, int pos_period,

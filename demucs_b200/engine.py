@@ -109,6 +109,19 @@ class PackedWeights:
                 put(f"{p}.g2", _interleave_glu(state[f"{p}.4.weight"].detach().float()))
                 put(f"{p}.be2", _interleave_glu(state[f"{p}.4.bias"].detach().float()))
                 put(f"{p}.scale", state[f"{p}.6.scale"])
+                if tc_forms:
+                    # tensor-core forms: hidden width padded to a multiple of 16 with zero rows / columns
+                    hid = state[f"{p}.0.weight"].shape[0]
+                    hp = (hid + 15) // 16 * 16
+
+                    def pad_rows(t):
+                        t = t.detach().float()
+                        return torch.cat([t, t.new_zeros((hp - hid,) + tuple(t.shape[1:]))], 0)
+                    put(f"{p}.w1p", pad_rows(self.t[f"{p}.w1"].cpu()))
+                    put(f"{p}.b1p", pad_rows(state[f"{p}.0.bias"]))
+                    put(f"{p}.g1p", pad_rows(state[f"{p}.1.weight"]))
+                    put(f"{p}.be1p", pad_rows(state[f"{p}.1.bias"]))
+                    put(f"{p}.w2p", pad_rows(self.t[f"{p}.w2"].cpu().t()).t())
 
         for i in range(cfg.depth):
             for name in ("encoder", "tencoder"):
@@ -245,26 +258,32 @@ class Engine:
         M = B * T * Fr
         slabs = B * Fr
         stat = (T * Fr, Fr, Fr)                      # slab(m) = b*Fr + fr
-        h = self._buf(key, f"dconv_h{tag}", M * hid)
+        tc = self.mode == "tf32"
+        hp = (hid + 15) // 16 * 16 if tc else hid      # tensor-core arm: h is stored 16-column padded
+        h = self._buf(key, f"dconv_h{tag}", M * hp)
         sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64)
         mr1 = self._buf(key, f"dconv_mr1{tag}", 2 * slabs)
         mr2 = self._buf(key, f"dconv_mr2{tag}", 2 * slabs)
+        sfx = "p" if tc else ""
         for dd in range(cfg.dconv_depth):
             p = f"{prefix}.dconv.layers.{dd}"
             dil = 2 ** dd
             # (1) h = conv3_dilated(x) and the GroupNorm statistics of h
             sums.zero_()
-            self._gemm(M=M, N=hid, Cin=C_, x=x, w=W[f"{p}.w1"], bias=W[f"{p}.b1"], out=h,
+            self._gemm(M=M, N=hp, Cin=C_, x=x, w=W[f"{p}.w1{sfx}"], bias=W[f"{p}.b1{sfx}"], out=h,
                        taps=((-dil, 0), (0, 0), (dil, 0)), I1=T, I0=Fr, J1=T, J0=Fr,
-                       xs=(T * Fr * C_, Fr * C_, C_, 1), os_=(T * Fr * hid, Fr * hid, hid),
-                       stats_out=sums, stat=stat, tc=False)
+                       xs=(T * Fr * C_, Fr * C_, C_, 1), os_=(T * Fr * hp, Fr * hp, hp),
+                       stats_out=sums, stat=stat, tc=tc)
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr1), slabs, float(T * hid), self._stream())
+            common = dict(M=M, N=2 * C_, Cin=hp, x=h, w=W[f"{p}.w2{sfx}"], bias=W[f"{p}.b2"], stat=stat, tc=tc)
+            if tc:   # TMA-fed operand: apply gelu(gn(.)) to the narrow h in place first
+                self._k("bd_gn_gelu_apply", ptr(h), ptr(mr1), ptr(W[f"{p}.g1p"]), ptr(W[f"{p}.be1p"]), M, hp,
+                        T * Fr, Fr, self._stream(), nbytes=8.0 * M * hp)
+            else:    # CUDA-core arm applies it while gathering the A operand
+                common.update(a_mode=_lib.A_GN_GELU, a_stats=mr1, a_gamma=W[f"{p}.g1"], a_beta=W[f"{p}.be1"])
             # (2) statistics of u = conv1x1(gelu(gn(h))) WITHOUT storing u: the expanded [.., 2C] tensor
             #     never touches HBM, it is recomputed from the 8x narrower h in (3)
             sums.zero_()
-            common = dict(M=M, N=2 * C_, Cin=hid, x=h, w=W[f"{p}.w2"], bias=W[f"{p}.b2"],
-                          a_mode=_lib.A_GN_GELU, a_stats=mr1, a_gamma=W[f"{p}.g1"], a_beta=W[f"{p}.be1"],
-                          stat=stat, tc=False)
             self._gemm(out=None, stats_out=sums, **common)
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr2), slabs, float(T * 2 * C_), self._stream())
             # (3) x += scale * GLU(gn(u)), in place

@@ -112,6 +112,10 @@ int bd_finalize_group_stats(const double* sums, float* mean_rstd, int slabs, dou
  * (m / rows_per_item) * slabs_per_item + m % slabs_per_item  (time: 1 slab per item; freq: one per bin). */
 int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float* gamma, const float* beta,
                   const float* scale, long long M, int C, long long rows_per_item, int slabs_per_item, void* stream);
+/* DConv inner activation (demucs.py:138-139): h[m, c] = gelu(GroupNorm(h))[m, c] in place, slab map as
+ * bd_dconv_tail.  Used by the tensor-core arm, whose TMA-fed A operand cannot be transformed on the fly. */
+int bd_gn_gelu_apply(float* h, const float* mean_rstd, const float* gamma, const float* beta, long long M, int C,
+                     long long rows_per_item, int slabs_per_item, void* stream);
 /* nn.LayerNorm(C) (transformer.py:434-436,591-592,597-598) with optional additive table
  * pos[(m % pos_period)*C + c] (positional embedding, transformer.py:655-663). y may alias x. */
 int bd_layer_norm(const float* x, float* y, const float* gamma, const float* beta, const float* pos,

@@ -176,6 +176,14 @@ def bd_dconv_tail(x, u, mr, gamma, beta, scale, M, Cc, rows_per_item, spi, strea
     xv += f32(scale, Cc) * (g[:, 0::2] * sigmoid(g[:, 1::2]))
 
 
+def bd_gn_gelu_apply(h, mr, gamma, beta, M, Cc, rows_per_item, spi, stream):
+    hv = f32(h, M * Cc).reshape(M, Cc)
+    m = np.arange(M)
+    slab = (m // rows_per_item) * spi + (m % spi)
+    st = f32(mr, 2 * (int(slab.max()) + 1)).reshape(-1, 2)[slab]
+    hv[:] = gelu((hv - st[:, :1]) * st[:, 1:2] * f32(gamma, Cc) + f32(beta, Cc))
+
+
 def bd_layer_norm(x, y, gamma, beta, pos, period, M, Cc, stream):
     xv = f32(x, M * Cc).reshape(M, Cc).astype(np.float64)
     mean = xv.mean(1, keepdims=True)
