@@ -51,9 +51,53 @@ __device__ __forceinline__ bool bd_epi_vec_ok(const bd_gemm_desc& d) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+// Memory-side operands of one 4-column group: output offset plus the residual / skip / embedding
+// values, fetched BEFORE any arithmetic so that a caller can put several groups' loads in flight
+// (the in-place residual update makes loads and stores alias, which stops the compiler from doing it).
+struct EpiMem {
+  long long o;       // output offset of the first stored element, -1: nothing to store
+  int no;
+  float4 resid, addend, rowbias;
+};
+
+__device__ __forceinline__ EpiMem bd_epi_fetch4(const bd_gemm_desc& d, const EpiRow& r, int n) {
+  EpiMem e;
+  e.resid = e.addend = e.rowbias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (d.act == BD_ACT_GLU) {
+    e.no = n >> 1;
+    const int Nout = d.N >> 1;
+    e.o = r.obase + (long long)r.i0 * d.os_0 + e.no;
+    if (d.rowbias) { const float2 t = ldg2(d.rowbias + (size_t)r.rb_row * Nout + e.no); e.rowbias.x = t.x; e.rowbias.y = t.y; }
+    if (d.resid) { const float2 t = ldg2(d.resid + e.o); e.resid.x = t.x; e.resid.y = t.y; }
+    if (d.addend) { const float2 t = ldg2(d.addend + e.o); e.addend.x = t.x; e.addend.y = t.y; }
+    return e;
+  }
+  int Nout = d.N;
+  e.no = n;
+  if (d.convt) {
+    const int Cout = d.N >> 2;
+    const int rr = n / Cout;
+    const int o0 = 4 * r.i0 + rr - (d.convt == 1 ? 2 : 0);
+    if (o0 < 0 || o0 >= d.O0) {
+      e.o = -1;
+      return e;
+    }
+    e.no = n - rr * Cout;
+    Nout = Cout;
+    e.o = r.obase + (long long)o0 * d.os_0 + e.no;
+  } else {
+    e.o = r.obase + (long long)r.i0 * d.os_0 + e.no;
+  }
+  if (d.rowbias) e.rowbias = ldg4(d.rowbias + (size_t)r.rb_row * Nout + e.no);
+  if (d.resid) e.resid = ldg4(d.resid + e.o);
+  if (d.addend) e.addend = ldg4(d.addend + e.o);
+  return e;
+}
+
 // Finish accumulator columns n..n+3 (n % 4 == 0, n + 3 < N) of row r.  Adds the stored values to (s, q).
-__device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRow& r, int n, float4 v, float& s,
-                                              float& q) {
+__device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiRow& r, int n, float4 v, const EpiMem& e,
+                                               float& s, float& q) {
+  if (e.o < 0) return;
   if (d.bias) {
     const float4 b = ldg4(d.bias + n);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -67,23 +111,14 @@ __device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRo
   }
   if (d.act == BD_ACT_GLU) {
     float2 o2 = make_float2(v.x * bd_sigmoid(v.y), v.z * bd_sigmoid(v.w));
-    const int no = n >> 1, Nout = d.N >> 1;
-    const long long o = r.obase + (long long)r.i0 * d.os_0 + no;
-    if (d.rowbias) {
-      const float2 rb = ldg2(d.rowbias + (size_t)r.rb_row * Nout + no);
-      o2.x += rb.x; o2.y += rb.y;
-    }
+    o2.x += e.rowbias.x; o2.y += e.rowbias.y;
     if (d.resid) {
-      const float2 rs = ldg2(d.resid + o);
       float2 sc = make_float2(1.f, 1.f);
-      if (d.scale) sc = ldg2(d.scale + no);
-      o2.x = fmaf(sc.x, o2.x, rs.x); o2.y = fmaf(sc.y, o2.y, rs.y);
+      if (d.scale) sc = ldg2(d.scale + e.no);
+      o2.x = fmaf(sc.x, o2.x, e.resid.x); o2.y = fmaf(sc.y, o2.y, e.resid.y);
     }
-    if (d.addend) {
-      const float2 ad = ldg2(d.addend + o);
-      o2.x += ad.x; o2.y += ad.y;
-    }
-    if (d.out) *reinterpret_cast<float2*>(d.out + o) = o2;
+    o2.x += e.addend.x; o2.y += e.addend.y;
+    if (d.out) *reinterpret_cast<float2*>(d.out + e.o) = o2;
     s += o2.x + o2.y;
     q = fmaf(o2.x, o2.x, fmaf(o2.y, o2.y, q));
     return;
@@ -91,36 +126,23 @@ __device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRo
   if (d.act == BD_ACT_GELU) {
     v.x = bd_gelu(v.x); v.y = bd_gelu(v.y); v.z = bd_gelu(v.z); v.w = bd_gelu(v.w);
   }
-  int no = n, Nout = d.N;
-  long long o;
-  if (d.convt) {
-    const int Cout = d.N >> 2;
-    const int rr = n / Cout;
-    const int o0 = 4 * r.i0 + rr - (d.convt == 1 ? 2 : 0);
-    if (o0 < 0 || o0 >= d.O0) return;
-    no = n - rr * Cout;
-    Nout = Cout;
-    o = r.obase + (long long)o0 * d.os_0 + no;
-  } else {
-    o = r.obase + (long long)r.i0 * d.os_0 + no;
-  }
-  if (d.rowbias) {
-    const float4 rb = ldg4(d.rowbias + (size_t)r.rb_row * Nout + no);
-    v.x += rb.x; v.y += rb.y; v.z += rb.z; v.w += rb.w;
-  }
+  v.x += e.rowbias.x; v.y += e.rowbias.y; v.z += e.rowbias.z; v.w += e.rowbias.w;
   if (d.resid) {
-    const float4 rs = ldg4(d.resid + o);
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (d.scale) sc = ldg4(d.scale + no);
-    v.x = fmaf(sc.x, v.x, rs.x); v.y = fmaf(sc.y, v.y, rs.y); v.z = fmaf(sc.z, v.z, rs.z); v.w = fmaf(sc.w, v.w, rs.w);
+    if (d.scale) sc = ldg4(d.scale + e.no);
+    v.x = fmaf(sc.x, v.x, e.resid.x); v.y = fmaf(sc.y, v.y, e.resid.y);
+    v.z = fmaf(sc.z, v.z, e.resid.z); v.w = fmaf(sc.w, v.w, e.resid.w);
   }
-  if (d.addend) {
-    const float4 ad = ldg4(d.addend + o);
-    v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
-  }
-  if (d.out) *reinterpret_cast<float4*>(d.out + o) = v;
+  v.x += e.addend.x; v.y += e.addend.y; v.z += e.addend.z; v.w += e.addend.w;
+  if (d.out) *reinterpret_cast<float4*>(d.out + e.o) = v;
   s += (v.x + v.y) + (v.z + v.w);
   q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+}
+
+__device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRow& r, int n, float4 v, float& s,
+                                              float& q) {
+  const EpiMem e = bd_epi_fetch4(d, r, n);
+  bd_epi_finish4(d, r, n, v, e, s, q);
 }
 
 // Scalar form: finish accumulator `acc` of column n (and `acc_gate` of column n+1 for GLU, n even).

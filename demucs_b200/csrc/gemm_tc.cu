@@ -231,32 +231,84 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    // TMEM rows come out one per lane; HBM wants a row's columns side by side.  Each warp dumps its 32 rows
+    // into the (now idle) pipeline shared memory, then walks them row by row with lane = 4-column group,
+    // so every global access of the fused epilogue is a contiguous run of the output row.
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const int i0 = i0s + (r & (g.R0 - 1)), i1 = i1s + (r >> g.log2R0);
     const bool row_ok = i0 < d.I0 && i1 < d.I1;
     const long long m = ((long long)b * d.I1 + i1) * d.I0 + i0;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar, 0);            // also: every MMA has finished reading the smem stages
     tcgen05_fence_after();
     EpiRow er;
+    er.obase = 0; er.i0 = 0; er.rb_row = 0; er.e_mean = 0.f; er.e_rstd = 1.f;
     if (row_ok) er = bd_epi_row(d, m);
+    const int my_slab = (d.stats_out && d.stat_mod != 1 && row_ok) ? bd_stat_slab(d, m) : -1;
     float ssum = 0.f, ssq = 0.f;
     const bool vec = bd_epi_vec_ok(d);
-    for (int c0 = 0; c0 < TBN; c0 += CW) {
-      if (n0 + c0 >= d.N) break;            // warp-uniform
-      uint32_t v[CW];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-      if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-      if (row_ok) {
-        if (vec) {
+    constexpr int LDT = TBN + 4;            // staging row pitch (floats): conflict-free float4 rows
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)quarter * 32 * LDT;
+    static_assert(4 * 32 * (TBN + 4) * 4 <= kStages * (kStageBytesA + kStageBytesB), "staging fits in the pipeline smem");
+    if (vec) {
+      for (int c0 = 0; c0 < TBN; c0 += CW) {
+        if (n0 + c0 >= d.N) break;          // warp-uniform
+        uint32_t v[CW];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 #pragma unroll
-          for (int j = 0; j < CW; j += 4) {
-            const int n = n0 + c0 + j;
-            if (n < d.N)
-              bd_epi_apply4(d, er, n, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), ssum, ssq);
+        for (int j = 0; j < CW; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * LDT + c0 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
+      }
+      __syncwarp();
+      const int n = n0 + 4 * lane;
+      const bool col_ok = 4 * lane < TBN && n < d.N;
+      constexpr int RB = 4;                 // rows whose memory operands are in flight together
+      for (int rr = 0; rr < 32; rr += RB) {
+        EpiRow row[RB];
+        EpiMem mem[RB];
+        bool ok[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int src = rr + u;
+          ok[u] = __shfl_sync(0xffffffffu, (int)row_ok, src) != 0;
+          row[u].obase = __shfl_sync(0xffffffffu, er.obase, src);
+          row[u].i0 = __shfl_sync(0xffffffffu, er.i0, src);
+          row[u].rb_row = __shfl_sync(0xffffffffu, er.rb_row, src);
+          row[u].e_mean = __shfl_sync(0xffffffffu, er.e_mean, src);
+          row[u].e_rstd = __shfl_sync(0xffffffffu, er.e_rstd, src);
+          if (ok[u] && col_ok) mem[u] = bd_epi_fetch4(d, row[u], n);
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          float rs = 0.f, rq = 0.f;
+          if (ok[u] && col_ok) {
+            const float4 a = *reinterpret_cast<const float4*>(stage + (rr + u) * LDT + 4 * lane);
+            bd_epi_finish4(d, row[u], n, a, mem[u], rs, rq);
           }
-        } else {
+          if (d.stats_out && d.stat_mod != 1) {   // per-row GroupNorm slab: reduce the row across the warp
+            rs = bd_warp_sum(rs);
+            rq = bd_warp_sum(rq);
+            const int sl = __shfl_sync(0xffffffffu, my_slab, rr + u);
+            if (lane == 0 && sl >= 0) {
+              atomicAdd(&d.stats_out[2 * (size_t)sl], (double)rs);
+              atomicAdd(&d.stats_out[2 * (size_t)sl + 1], (double)rq);
+            }
+          } else {
+            ssum += rs;
+            ssq += rq;
+          }
+        }
+      }
+    } else {
+      for (int c0 = 0; c0 < TBN; c0 += CW) {
+        if (n0 + c0 >= d.N) break;
+        uint32_t v[CW];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        if (row_ok) {
 #pragma unroll
           for (int j = 0; j < CW; ++j) {
             const int n = n0 + c0 + j;
@@ -270,20 +322,16 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
           }
         }
       }
+      if (d.stats_out && d.stat_mod != 1 && row_ok) {
+        atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)ssum);
+        atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)ssq);
+      }
     }
-    if (d.stats_out) {
-      if (d.stat_mod != 1) {                // frequency branch: the GroupNorm slab changes with every row
-        if (row_ok) {
-          const int sl = bd_stat_slab(d, m);
-          atomicAdd(&d.stats_out[2 * (size_t)sl], (double)ssum);
-          atomicAdd(&d.stats_out[2 * (size_t)sl + 1], (double)ssq);
-        }
-      } else {
-        double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
-        if (lane == 0) {
-          red[quarter] = ds;
-          red[4 + quarter] = dq;
-        }
+    if (d.stats_out && d.stat_mod == 1) {
+      double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
+      if (lane == 0) {
+        red[quarter] = ds;
+        red[4 + quarter] = dq;
       }
     }
   }

@@ -270,12 +270,18 @@ class Engine:
             dil = 2 ** dd
             # (1) h = conv3_dilated(x) and the GroupNorm statistics of h
             sums.zero_()
+            if Fr == 1:   # time branch: positions are the fast axis, one GroupNorm item per batch item
+                geo = dict(taps=((0, -dil), (0, 0), (0, dil)), I1=1, I0=T, J1=1, J0=T,
+                           xs=(T * C_, 0, C_, 1), os_=(T * hp, 0, hp))
+            else:         # frequency branch [B, T, Fr, C]: the conv runs along T, the slow axis
+                geo = dict(taps=((-dil, 0), (0, 0), (dil, 0)), I1=T, I0=Fr, J1=T, J0=Fr,
+                           xs=(T * Fr * C_, Fr * C_, C_, 1), os_=(T * Fr * hp, Fr * hp, hp))
             self._gemm(M=M, N=hp, Cin=C_, x=x, w=W[f"{p}.w1{sfx}"], bias=W[f"{p}.b1{sfx}"], out=h,
-                       taps=((-dil, 0), (0, 0), (dil, 0)), I1=T, I0=Fr, J1=T, J0=Fr,
-                       xs=(T * Fr * C_, Fr * C_, C_, 1), os_=(T * Fr * hp, Fr * hp, hp),
-                       stats_out=sums, stat=stat, tc=tc)
+                       stats_out=sums, stat=stat, tc=tc, **geo)
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr1), slabs, float(T * hid), self._stream())
             common = dict(M=M, N=2 * C_, Cin=hp, x=h, w=W[f"{p}.w2{sfx}"], bias=W[f"{p}.b2"], stat=stat, tc=tc)
+            if Fr == 1:
+                common.update(I1=1, I0=T, J1=1, J0=T, xs=(T * hp, 0, hp, 1), os_=(T * C_, 0, C_))
             if tc:   # TMA-fed operand: apply gelu(gn(.)) to the narrow h in place first
                 self._k("bd_gn_gelu_apply", ptr(h), ptr(mr1), ptr(W[f"{p}.g1p"]), ptr(W[f"{p}.be1p"]), M, hp,
                         T * Fr, Fr, self._stream(), nbytes=8.0 * M * hp)
