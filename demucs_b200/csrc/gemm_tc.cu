@@ -41,11 +41,26 @@ struct Cfg {
   static constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
   static constexpr int kStagesRaw = 98304 / (kStageBytesA + kStageBytesB);   // ~96 KB: two CTAs per SM
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 32 * (TBN + 4) * 4;
+  static constexpr int kTailBytes = 256 /*barriers*/ + 128 * 32 /*RowInfo*/;
+  static constexpr int smem_bytes(int stages) {
+    int pipe = stages * (kStageBytesA + kStageBytesB);
+    return (pipe > kStagingBytes ? pipe : kStagingBytes) + 1024 /*align slack*/ + kTailBytes;
+  }
+  static constexpr int kSmemBytes = smem_bytes(kStages);
   static constexpr int kTmemCols = TBN < 32 ? 32 : TBN;
 };
 
+struct RowInfo {           // per-row epilogue constants, parked in shared memory (32 bytes)
+  long long obase;
+  int i0;                  // -1: row outside the problem
+  int rb_row;
+  float e_mean, e_rstd;
+  int pad0, pad1;
+};
+
 struct TileGeom {
+  int stages;            // smem pipeline depth actually used (<= Cfg::kStages; short K loops need fewer)
   int R0, R1;            // tile = R1 rows (i1) x R0 positions (i0), R0 * R1 == 128, powers of two
   int log2R0;
   int blocks0, blocks1;  // tiles along i0 / i1 per item
@@ -157,9 +172,12 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
   constexpr int CW = TBN < 32 ? TBN : 32;            // columns per TMEM load
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nstages = g.stages;
+  constexpr int kStagingBytes = 4 * 32 * (TBN + 4) * 4;   // epilogue staging, aliases the pipeline buffers
+  const int pipe_bytes = nstages * (kStageBytesA + kStageBytesB);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kStageBytesA;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * kStageBytesB);
+  uint8_t* sB = smem + nstages * kStageBytesA;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (pipe_bytes > kStagingBytes ? pipe_bytes : kStagingBytes));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -198,8 +216,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     if (lane == 0) {
       int tap = 0, cb = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
+        const int s = kb % nstages;
+        const uint32_t ph = (kb / nstages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
         // A: the tap-shifted window of the activation tensor; out-of-range rows/positions read as zero
@@ -216,8 +234,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TBM, TBN);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
+        const int s = kb % nstages;
+        const uint32_t ph = (kb / nstages) & 1;
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
         const uint64_t adesc = make_kmajor_desc<TBK>(sA + s * kStageBytesA);
@@ -244,13 +262,19 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     EpiRow er;
     er.obase = 0; er.i0 = 0; er.rb_row = 0; er.e_mean = 0.f; er.e_rstd = 1.f;
     if (row_ok) er = bd_epi_row(d, m);
-    const int my_slab = (d.stats_out && d.stat_mod != 1 && row_ok) ? bd_stat_slab(d, m) : -1;
+    const bool row_stats = d.stats_out && d.stat_mod != 1;
+    const int my_slab = (row_stats && row_ok) ? bd_stat_slab(d, m) : -1;
     float ssum = 0.f, ssq = 0.f;
     const bool vec = bd_epi_vec_ok(d);
     constexpr int LDT = TBN + 4;            // staging row pitch (floats): conflict-free float4 rows
     float* stage = reinterpret_cast<float*>(smem) + (size_t)quarter * 32 * LDT;
-    static_assert(4 * 32 * (TBN + 4) * 4 <= kStages * (kStageBytesA + kStageBytesB), "staging fits in the pipeline smem");
+    RowInfo* rinfo = reinterpret_cast<RowInfo*>(tmem_slot + 4) + quarter * 32;
     if (vec) {
+      rinfo[lane].obase = er.obase;
+      rinfo[lane].i0 = row_ok ? er.i0 : -1;
+      rinfo[lane].rb_row = er.rb_row;
+      rinfo[lane].e_mean = er.e_mean;
+      rinfo[lane].e_rstd = er.e_rstd;
       for (int c0 = 0; c0 < TBN; c0 += CW) {
         if (n0 + c0 >= d.N) break;          // warp-uniform
         uint32_t v[CW];
@@ -263,43 +287,55 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
                           __uint_as_float(v[j + 3]));
       }
       __syncwarp();
-      const int n = n0 + 4 * lane;
-      const bool col_ok = 4 * lane < TBN && n < d.N;
-      constexpr int RB = 4;                 // rows whose memory operands are in flight together
-      for (int rr = 0; rr < 32; rr += RB) {
+      // lane -> (row within group, 4-column group): a warp instruction covers RPI rows x TBN columns
+      constexpr int CG = TBN / 4 < 32 ? TBN / 4 : 32;
+      constexpr int RPI = 32 / CG;
+      constexpr int RB = 4;                 // row groups whose memory operands are in flight together
+      const int cg = lane % CG, rsub = lane / CG;
+      const int n = n0 + 4 * cg;
+      const bool col_ok = n < d.N;
+      for (int it = 0; it < 32 / RPI; it += RB) {
         EpiRow row[RB];
         EpiMem mem[RB];
         bool ok[RB];
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
-          const int src = rr + u;
-          ok[u] = __shfl_sync(0xffffffffu, (int)row_ok, src) != 0;
-          row[u].obase = __shfl_sync(0xffffffffu, er.obase, src);
-          row[u].i0 = __shfl_sync(0xffffffffu, er.i0, src);
-          row[u].rb_row = __shfl_sync(0xffffffffu, er.rb_row, src);
-          row[u].e_mean = __shfl_sync(0xffffffffu, er.e_mean, src);
-          row[u].e_rstd = __shfl_sync(0xffffffffu, er.e_rstd, src);
-          if (ok[u] && col_ok) mem[u] = bd_epi_fetch4(d, row[u], n);
+          const int rloc = (it + u) * RPI + rsub;
+          const RowInfo ri = rinfo[rloc];
+          row[u].obase = ri.obase; row[u].i0 = ri.i0; row[u].rb_row = ri.rb_row;
+          row[u].e_mean = ri.e_mean; row[u].e_rstd = ri.e_rstd;
+          ok[u] = (it + u) * RPI < 32 && ri.i0 >= 0 && col_ok;
+          if (ok[u]) mem[u] = bd_epi_fetch4(d, row[u], n);
         }
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
+          const int rloc = (it + u) * RPI + rsub;
           float rs = 0.f, rq = 0.f;
-          if (ok[u] && col_ok) {
-            const float4 a = *reinterpret_cast<const float4*>(stage + (rr + u) * LDT + 4 * lane);
+          if (ok[u]) {
+            const float4 a = *reinterpret_cast<const float4*>(stage + rloc * LDT + 4 * cg);
             bd_epi_finish4(d, row[u], n, a, mem[u], rs, rq);
           }
-          if (d.stats_out && d.stat_mod != 1) {   // per-row GroupNorm slab: reduce the row across the warp
-            rs = bd_warp_sum(rs);
-            rq = bd_warp_sum(rq);
-            const int sl = __shfl_sync(0xffffffffu, my_slab, rr + u);
-            if (lane == 0 && sl >= 0) {
-              atomicAdd(&d.stats_out[2 * (size_t)sl], (double)rs);
-              atomicAdd(&d.stats_out[2 * (size_t)sl + 1], (double)rq);
-            }
+          if (row_stats) {                  // park the partial sums in the (consumed) staging row
+            __syncwarp();                   // every lane has read its accumulators of this row group
+            if ((it + u) * RPI < 32) *reinterpret_cast<float2*>(stage + rloc * LDT + 2 * cg) = make_float2(rs, rq);
           } else {
             ssum += rs;
             ssq += rq;
           }
+        }
+      }
+      if (row_stats) {                      // lane = row again: one pair of atomics per row, all rows in parallel
+        __syncwarp();
+        float rs = 0.f, rq = 0.f;
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+          const float2 t = *reinterpret_cast<const float2*>(stage + lane * LDT + 2 * c);
+          rs += t.x;
+          rq += t.y;
+        }
+        if (my_slab >= 0) {
+          atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)rs);
+          atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)rq);
         }
       }
     } else {
@@ -322,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
           }
         }
       }
-      if (d.stats_out && d.stat_mod != 1 && row_ok) {
+      if (row_stats && row_ok) {
         atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)ssum);
         atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)ssq);
       }
@@ -410,7 +446,10 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
     configured = true;
   }
   dim3 grid((unsigned)((long long)items * g.blocks1 * g.blocks0), (d.N + TBN - 1) / TBN);
-  conv_gemm_tc_kernel<TBK, TBN><<<grid, kThreads, C_::kSmemBytes, st>>>(map_a, map_b, d, g);
+  TileGeom gg = g;
+  const int nkb = d.taps * g.cpb;
+  gg.stages = nkb < C_::kStages ? nkb : C_::kStages;
+  conv_gemm_tc_kernel<TBK, TBN><<<grid, kThreads, C_::smem_bytes(gg.stages), st>>>(map_a, map_b, d, gg);
   return bd_check_launch("conv_gemm_tc_kernel");
 }
 
