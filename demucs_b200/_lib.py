@@ -13,7 +13,7 @@ import typing as tp
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdemucs_b200.so")
-SOURCES = ["api.cu", "spectral.cu", "gemm_simt.cu", "gemm_tc.cu", "norm.cu", "attention.cu",
+SOURCES = ["api.cu", "spectral.cu", "gemm_simt.cu", "gemm_tc.cu", "norm.cu", "dconv.cu", "attention.cu",
            "ola.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -60,6 +60,8 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_conv_gemm_arm": [C.POINTER(GemmDesc)],
     "bd_finalize_group_stats": [_P, _P, _I, _D, _P],
     "bd_dconv_tail": [_P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
+    "bd_dconv_expand_stats": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
+    "bd_dconv_expand_update": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "bd_gn_gelu_apply": [_P, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "bd_layer_norm": [_P, _P, _P, _P, _P, _I, _LL, _I, _P],
     "bd_item_stats": [_P, _P, _I, _LL, _P],

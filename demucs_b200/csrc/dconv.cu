@@ -1,0 +1,144 @@
+// DConv expansion stage (reference demucs/demucs.py:138-142,151-153 + LayerScale transformer.py:236-255):
+//     g = gelu(GroupNorm(h));  u = W2 g + b2  (hidden -> 2C, 1x1 conv);  x += scale * GLU(GroupNorm(u))
+// The [.., 2C] tensor u is 16x wider than h and never touches HBM: pass 1 (statistics) and pass 2
+// (update) both recompute it from the narrow h.  With K = C/8 in 6..48 the contraction is far too thin
+// for a tensor-core tile (the epilogue is the whole kernel), so this is a CUDA-core kernel shaped by
+// HBM traffic: one thread = one row, the row's g vector lives in registers, W2 (transposed, <=147 KB)
+// is broadcast from shared memory as float4, and x is updated in place one float4 at a time.
+//   traffic / row: pass 1 reads hid floats; pass 2 reads hid + C and writes C floats.
+#include "common.cuh"
+#include "../../include/demucs_b200.h"
+
+namespace {
+
+constexpr int DC_THREADS = 128;
+constexpr int MAX_HID = 48;
+
+template <int HID_T, bool FINAL>
+__global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
+    const float* __restrict__ h, int ldh, int hid_rt, const float* __restrict__ mr1, const float* __restrict__ g1,
+    const float* __restrict__ be1, const float* __restrict__ w2t /*[hid][2C] interleaved*/, const float* __restrict__ b2,
+    double* __restrict__ sums2, const float* __restrict__ mr2, const float* __restrict__ g2, const float* __restrict__ be2,
+    const float* __restrict__ scale, float* __restrict__ x, long long M, int C, long long rows_per_item,
+    int slabs_per_item) {
+  extern __shared__ __align__(16) float sm[];
+  const int hid = HID_T > 0 ? HID_T : hid_rt;
+  const int N = 2 * C;
+  float* sW = sm;                         // [hid][N]
+  float* sB = sW + hid * N;               // [N]
+  float* sG = sB + N;                     // [N]   (FINAL)
+  float* sBe = sG + N;                    // [N]   (FINAL)
+  float* sS = sBe + N;                    // [C]   (FINAL)
+  for (int i = threadIdx.x; i < hid * N; i += DC_THREADS) sW[i] = __ldg(w2t + i);
+  for (int i = threadIdx.x; i < N; i += DC_THREADS) {
+    sB[i] = __ldg(b2 + i);
+    if (FINAL) {
+      sG[i] = __ldg(g2 + i);
+      sBe[i] = __ldg(be2 + i);
+    }
+  }
+  if (FINAL)
+    for (int i = threadIdx.x; i < C; i += DC_THREADS) sS[i] = __ldg(scale + i);
+  __syncthreads();
+
+  for (long long m = (long long)blockIdx.x * DC_THREADS + threadIdx.x; m < M; m += (long long)gridDim.x * DC_THREADS) {
+    const long long slab = (m / rows_per_item) * slabs_per_item + (m % slabs_per_item);
+    const float mean1 = __ldg(mr1 + 2 * slab), rstd1 = __ldg(mr1 + 2 * slab + 1);
+    float g[HID_T > 0 ? HID_T : MAX_HID];
+    const float* hr = h + m * ldh;
+#pragma unroll
+    for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k)
+      if (k < hid) g[k] = bd_gelu(fmaf((__ldg(hr + k) - mean1) * rstd1, __ldg(g1 + k), __ldg(be1 + k)));
+    float mean2 = 0.f, rstd2 = 1.f;
+    if (FINAL) {
+      mean2 = __ldg(mr2 + 2 * slab);
+      rstd2 = __ldg(mr2 + 2 * slab + 1);
+    }
+    float s = 0.f, q = 0.f;
+    float* xr = FINAL ? x + m * C : nullptr;
+    for (int n = 0; n < N; n += 4) {      // 4 interleaved columns = (value, gate) of 2 channels
+      float4 u = *reinterpret_cast<const float4*>(sB + n);
+#pragma unroll
+      for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k) {
+        if (k < hid) {
+          const float4 w = *reinterpret_cast<const float4*>(sW + k * N + n);
+          u.x = fmaf(w.x, g[k], u.x); u.y = fmaf(w.y, g[k], u.y);
+          u.z = fmaf(w.z, g[k], u.z); u.w = fmaf(w.w, g[k], u.w);
+        }
+      }
+      if (FINAL) {
+        const float4 ga = *reinterpret_cast<const float4*>(sG + n), be = *reinterpret_cast<const float4*>(sBe + n);
+        const float a0 = fmaf((u.x - mean2) * rstd2, ga.x, be.x), t0 = fmaf((u.y - mean2) * rstd2, ga.y, be.y);
+        const float a1 = fmaf((u.z - mean2) * rstd2, ga.z, be.z), t1 = fmaf((u.w - mean2) * rstd2, ga.w, be.w);
+        const float2 sc = *reinterpret_cast<const float2*>(sS + (n >> 1));
+        float2* xp = reinterpret_cast<float2*>(xr + (n >> 1));
+        float2 xv = *xp;
+        xv.x = fmaf(sc.x, a0 * bd_sigmoid(t0), xv.x);
+        xv.y = fmaf(sc.y, a1 * bd_sigmoid(t1), xv.y);
+        *xp = xv;
+      } else {
+        s += (u.x + u.y) + (u.z + u.w);
+        q = fmaf(u.x, u.x, fmaf(u.y, u.y, fmaf(u.z, u.z, fmaf(u.w, u.w, q))));
+      }
+    }
+    if (!FINAL) {
+      atomicAdd(&sums2[2 * slab], (double)s);
+      atomicAdd(&sums2[2 * slab + 1], (double)q);
+    }
+  }
+}
+
+template <bool FINAL>
+int launch_expand(const float* h, int ldh, int hid, const float* mr1, const float* g1, const float* be1, const float* w2t,
+                  const float* b2, double* sums2, const float* mr2, const float* g2, const float* be2, const float* scale,
+                  float* x, long long M, int C, long long rpi, int spi, cudaStream_t st) {
+  const int smem = (hid * 2 * C + 2 * C * 3 + C) * (int)sizeof(float);
+  int grid = (int)((M + DC_THREADS - 1) / DC_THREADS);
+  const int cap = 148 * (smem > 96 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 8) * 2;   // grid-stride: weights staged once per CTA
+  if (grid > cap) grid = cap;
+#define BD_DC_CASE(H)                                                                                             \
+  if (hid == H) {                                                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(dconv_expand_kernel<H, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         smem);                                                                   \
+    if (e != cudaSuccess) {                                                                                       \
+      bd_set_error("bd_dconv_expand: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                           \
+      return BD_ERR_CUDA;                                                                                         \
+    }                                                                                                             \
+    dconv_expand_kernel<H, FINAL><<<grid, DC_THREADS, smem, st>>>(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2,  \
+                                                                  be2, scale, x, M, C, rpi, spi);                 \
+    return bd_check_launch("dconv_expand_kernel");                                                                \
+  }
+  BD_DC_CASE(6) BD_DC_CASE(12) BD_DC_CASE(24) BD_DC_CASE(48)
+#undef BD_DC_CASE
+  cudaError_t e = cudaFuncSetAttribute(dconv_expand_kernel<0, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    bd_set_error("bd_dconv_expand: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return BD_ERR_CUDA;
+  }
+  dconv_expand_kernel<0, FINAL><<<grid, DC_THREADS, smem, st>>>(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2, be2,
+                                                                scale, x, M, C, rpi, spi);
+  return bd_check_launch("dconv_expand_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
+                          const float* beta1, const float* w2t, const float* b2, double* sums2, long long M, int C,
+                          long long rows_per_item, int slabs_per_item, void* stream) {
+  BD_REQUIRE(hid > 0 && hid <= MAX_HID && C % 2 == 0 && ldh >= hid && M > 0, "bd_dconv_expand_stats: bad sizes (hid=%d C=%d)", hid, C);
+  return launch_expand<false>(h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, sums2, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream);
+}
+
+int bd_dconv_expand_update(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
+                           const float* beta1, const float* w2t, const float* b2, const float* mean_rstd2,
+                           const float* gamma2, const float* beta2, const float* scale, float* x, long long M, int C,
+                           long long rows_per_item, int slabs_per_item, void* stream) {
+  BD_REQUIRE(hid > 0 && hid <= MAX_HID && C % 2 == 0 && ldh >= hid && M > 0, "bd_dconv_expand_update: bad sizes (hid=%d C=%d)", hid, C);
+  return launch_expand<true>(h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, nullptr, mean_rstd2, gamma2, beta2, scale, x,
+                             M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -94,16 +94,40 @@ __device__ __forceinline__ EpiMem bd_epi_fetch4(const bd_gemm_desc& d, const Epi
   return e;
 }
 
-// Finish accumulator columns n..n+3 (n % 4 == 0, n + 3 < N) of row r.  Adds the stored values to (s, q).
-__device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiRow& r, int n, float4 v, const EpiMem& e,
-                                               float& s, float& q) {
-  if (e.o < 0) return;
-  if (d.bias) {
-    const float4 b = ldg4(d.bias + n);
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-  }
+// Column-side operands of a 4-column group (bias, GroupNorm affine, LayerScale): they depend on n only,
+// so a thread that keeps its column group across rows loads them once.
+struct EpiCol {
+  float4 bias, gamma, beta, scale;
+};
+
+__device__ __forceinline__ EpiCol bd_epi_cols4(const bd_gemm_desc& d, int n) {
+  EpiCol c;
+  c.bias = d.bias ? ldg4(d.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+  c.gamma = c.beta = make_float4(0.f, 0.f, 0.f, 0.f);
   if (d.e_stats) {
-    const float4 g = ldg4(d.e_gamma + n), be = ldg4(d.e_beta + n);
+    c.gamma = ldg4(d.e_gamma + n);
+    c.beta = ldg4(d.e_beta + n);
+  }
+  c.scale = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (d.resid && d.scale) {
+    if (d.act == BD_ACT_GLU) {
+      const float2 t = ldg2(d.scale + (n >> 1));
+      c.scale.x = t.x; c.scale.y = t.y;
+    } else {
+      const int no = d.convt ? n % (d.N >> 2) : n;
+      c.scale = ldg4(d.scale + no);
+    }
+  }
+  return c;
+}
+
+// Finish accumulator columns n..n+3 (n % 4 == 0, n + 3 < N) of row r.  Adds the stored values to (s, q).
+__device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiRow& r, const EpiCol& c, float4 v,
+                                               const EpiMem& e, float& s, float& q) {
+  if (e.o < 0) return;
+  v.x += c.bias.x; v.y += c.bias.y; v.z += c.bias.z; v.w += c.bias.w;
+  if (d.e_stats) {
+    const float4 g = c.gamma, be = c.beta;
     v.x = fmaf((v.x - r.e_mean) * r.e_rstd, g.x, be.x);
     v.y = fmaf((v.y - r.e_mean) * r.e_rstd, g.y, be.y);
     v.z = fmaf((v.z - r.e_mean) * r.e_rstd, g.z, be.z);
@@ -113,9 +137,7 @@ __device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiR
     float2 o2 = make_float2(v.x * bd_sigmoid(v.y), v.z * bd_sigmoid(v.w));
     o2.x += e.rowbias.x; o2.y += e.rowbias.y;
     if (d.resid) {
-      float2 sc = make_float2(1.f, 1.f);
-      if (d.scale) sc = ldg2(d.scale + e.no);
-      o2.x = fmaf(sc.x, o2.x, e.resid.x); o2.y = fmaf(sc.y, o2.y, e.resid.y);
+      o2.x = fmaf(c.scale.x, o2.x, e.resid.x); o2.y = fmaf(c.scale.y, o2.y, e.resid.y);
     }
     o2.x += e.addend.x; o2.y += e.addend.y;
     if (d.out) *reinterpret_cast<float2*>(d.out + e.o) = o2;
@@ -128,10 +150,8 @@ __device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiR
   }
   v.x += e.rowbias.x; v.y += e.rowbias.y; v.z += e.rowbias.z; v.w += e.rowbias.w;
   if (d.resid) {
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (d.scale) sc = ldg4(d.scale + e.no);
-    v.x = fmaf(sc.x, v.x, e.resid.x); v.y = fmaf(sc.y, v.y, e.resid.y);
-    v.z = fmaf(sc.z, v.z, e.resid.z); v.w = fmaf(sc.w, v.w, e.resid.w);
+    v.x = fmaf(c.scale.x, v.x, e.resid.x); v.y = fmaf(c.scale.y, v.y, e.resid.y);
+    v.z = fmaf(c.scale.z, v.z, e.resid.z); v.w = fmaf(c.scale.w, v.w, e.resid.w);
   }
   v.x += e.addend.x; v.y += e.addend.y; v.z += e.addend.z; v.w += e.addend.w;
   if (d.out) *reinterpret_cast<float4*>(d.out + e.o) = v;
@@ -139,10 +159,10 @@ __device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiR
   q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
 }
 
-__device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRow& r, int n, float4 v, float& s,
-                                              float& q) {
+__device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRow& r, const EpiCol& c, int n, float4 v,
+                                              float& s, float& q) {
   const EpiMem e = bd_epi_fetch4(d, r, n);
-  bd_epi_finish4(d, r, n, v, e, s, q);
+  bd_epi_finish4(d, r, c, v, e, s, q);
 }
 
 // Scalar form: finish accumulator `acc` of column n (and `acc_gate` of column n+1 for GLU, n even).

@@ -232,6 +232,14 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
   // threads that share it and issues its own pair of atomics.
   const bool row_stats = d.stats_out && d.stat_mod != 1;
   const bool vec = bd_epi_vec_ok(d);
+  EpiCol ecol[TN >= 4 ? TN / 4 : 1];
+  if (TN >= 4 && vec) {
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      const int n = n0 + col_of(j);
+      if (n < d.N) ecol[j / 4] = bd_epi_cols4(d, n);
+    }
+  }
   double ssum = 0.0, ssq = 0.0;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -245,8 +253,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
 #pragma unroll
         for (int j = 0; j < TN; j += 4) {
           const int n = n0 + col_of(j);
-          if (n < d.N) bd_epi_apply4(d, er, n, make_float4(acc[i][j], acc[i][(j + 1) % TN], acc[i][(j + 2) % TN],
-                                                           acc[i][(j + 3) % TN]), rs, rq);
+          if (n < d.N) bd_epi_apply4(d, er, ecol[j / 4], n, make_float4(acc[i][j], acc[i][(j + 1) % TN],
+                                                                        acc[i][(j + 2) % TN], acc[i][(j + 3) % TN]), rs, rq);
         }
       } else {
 #pragma unroll

@@ -91,6 +91,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > kSpinLimit) __trap();
   }
 }
+// Same, for waiters that are not on the critical path (epilogue warps parked during the main loop, the
+// producer waiting for a free stage): back off between polls so that they do not compete for issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(64);
+    if (++spins > kSpinLimit) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -218,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % nstages;
         const uint32_t ph = (kb / nstages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
         // A: the tap-shifted window of the activation tensor; out-of-range rows/positions read as zero
         tma_load_4d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, i0s + d.d0[tap], i1s + d.d1[tap], b);
@@ -257,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     const int i0 = i0s + (r & (g.R0 - 1)), i1 = i1s + (r >> g.log2R0);
     const bool row_ok = i0 < d.I0 && i1 < d.I1;
     const long long m = ((long long)b * d.I1 + i1) * d.I0 + i0;
-    mbar_wait(tmem_full_bar, 0);            // also: every MMA has finished reading the smem stages
+    mbar_wait_relaxed(tmem_full_bar, 0);    // also: every MMA has finished reading the smem stages
     tcgen05_fence_after();
     EpiRow er;
     er.obase = 0; er.i0 = 0; er.rb_row = 0; er.e_mean = 0.f; er.e_rstd = 1.f;
@@ -294,6 +311,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
       const int cg = lane % CG, rsub = lane / CG;
       const int n = n0 + 4 * cg;
       const bool col_ok = n < d.N;
+      EpiCol ecol;
+      if (col_ok) ecol = bd_epi_cols4(d, n);
       for (int it = 0; it < 32 / RPI; it += RB) {
         EpiRow row[RB];
         EpiMem mem[RB];
@@ -313,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
           float rs = 0.f, rq = 0.f;
           if (ok[u]) {
             const float4 a = *reinterpret_cast<const float4*>(stage + rloc * LDT + 4 * cg);
-            bd_epi_finish4(d, row[u], n, a, mem[u], rs, rq);
+            bd_epi_finish4(d, row[u], ecol, a, mem[u], rs, rq);
           }
           if (row_stats) {                  // park the partial sums in the (consumed) staging row
             __syncwarp();                   // every lane has read its accumulators of this row group

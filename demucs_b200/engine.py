@@ -109,6 +109,7 @@ class PackedWeights:
                 put(f"{p}.g2", _interleave_glu(state[f"{p}.4.weight"].detach().float()))
                 put(f"{p}.be2", _interleave_glu(state[f"{p}.4.bias"].detach().float()))
                 put(f"{p}.scale", state[f"{p}.6.scale"])
+                put(f"{p}.w2t", self.t[f"{p}.w2"].cpu().t())      # [hid, 2C] for the dedicated expansion kernels
                 if tc_forms:
                     # tensor-core forms: hidden width padded to a multiple of 16 with zero rows / columns
                     hid = state[f"{p}.0.weight"].shape[0]
@@ -279,22 +280,20 @@ class Engine:
             self._gemm(M=M, N=hp, Cin=C_, x=x, w=W[f"{p}.w1{sfx}"], bias=W[f"{p}.b1{sfx}"], out=h,
                        stats_out=sums, stat=stat, tc=tc, **geo)
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr1), slabs, float(T * hid), self._stream())
-            common = dict(M=M, N=2 * C_, Cin=hp, x=h, w=W[f"{p}.w2{sfx}"], bias=W[f"{p}.b2"], stat=stat, tc=tc)
-            if Fr == 1:
-                common.update(I1=1, I0=T, J1=1, J0=T, xs=(T * hp, 0, hp, 1), os_=(T * C_, 0, C_))
-            if tc:   # TMA-fed operand: apply gelu(gn(.)) to the narrow h in place first
-                self._k("bd_gn_gelu_apply", ptr(h), ptr(mr1), ptr(W[f"{p}.g1p"]), ptr(W[f"{p}.be1p"]), M, hp,
-                        T * Fr, Fr, self._stream(), nbytes=8.0 * M * hp)
-            else:    # CUDA-core arm applies it while gathering the A operand
-                common.update(a_mode=_lib.A_GN_GELU, a_stats=mr1, a_gamma=W[f"{p}.g1"], a_beta=W[f"{p}.be1"])
-            # (2) statistics of u = conv1x1(gelu(gn(h))) WITHOUT storing u: the expanded [.., 2C] tensor
-            #     never touches HBM, it is recomputed from the 8x narrower h in (3)
+            # (2) statistics of u = conv1x1(gelu(gn(h))) WITHOUT storing u: the expanded [.., 2C] tensor never
+            #     touches HBM, both passes recompute it from the 8x narrower h (csrc/dconv.cu)
             sums.zero_()
-            self._gemm(out=None, stats_out=sums, **common)
+            self._k("bd_dconv_expand_stats", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
+                    ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(sums), M, C_, T * Fr, Fr, self._stream(),
+                    nbytes=4.0 * M * hid, flops=4.0 * M * hid * C_, label="dconv_expand_stats",
+                    detail=f"M={M} C={C_} hid={hid}")
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr2), slabs, float(T * 2 * C_), self._stream())
             # (3) x += scale * GLU(gn(u)), in place
-            self._gemm(out=x, e_stats=mr2, e_gamma=W[f"{p}.g2"], e_beta=W[f"{p}.be2"], act=_lib.ACT_GLU,
-                       resid=x, scale=W[f"{p}.scale"], **common)
+            self._k("bd_dconv_expand_update", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
+                    ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(mr2), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
+                    ptr(W[f"{p}.scale"]), ptr(x), M, C_, T * Fr, Fr, self._stream(),
+                    nbytes=4.0 * M * (hid + 2 * C_), flops=4.0 * M * hid * C_, label="dconv_expand_update",
+                    detail=f"M={M} C={C_} hid={hid}")
 
     def _attention_block(self, key, x, kv_src, p: str, attn: str, B: int, Tq: int, Tk: int, tag: str):
         """x += gamma_1 * MHA(q=x_normed, k=v=kv_normed); both inputs are already layer-normed."""

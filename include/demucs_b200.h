@@ -112,6 +112,18 @@ int bd_finalize_group_stats(const double* sums, float* mean_rstd, int slabs, dou
  * (m / rows_per_item) * slabs_per_item + m % slabs_per_item  (time: 1 slab per item; freq: one per bin). */
 int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float* gamma, const float* beta,
                   const float* scale, long long M, int C, long long rows_per_item, int slabs_per_item, void* stream);
+/* DConv expansion stage (demucs.py:138-142,151-153), dedicated HBM-shaped kernels; slab map as bd_dconv_tail.
+ *   h [M, ldh] holds the conv3 output (first `hid` columns), w2t [hid, 2C] is the transposed 1x1 weight with
+ *   interleaved (value, gate) columns, b2/gamma2/beta2 [2C] interleaved likewise.
+ * _stats : sums2[slab] += (sum, sumsq) of u = W2 gelu(gn1(h)) + b2            (u is never stored)
+ * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place) */
+int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
+                          const float* beta1, const float* w2t, const float* b2, double* sums2, long long M, int C,
+                          long long rows_per_item, int slabs_per_item, void* stream);
+int bd_dconv_expand_update(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
+                           const float* beta1, const float* w2t, const float* b2, const float* mean_rstd2,
+                           const float* gamma2, const float* beta2, const float* scale, float* x, long long M, int C,
+                           long long rows_per_item, int slabs_per_item, void* stream);
 /* DConv inner activation (demucs.py:138-139): h[m, c] = gelu(GroupNorm(h))[m, c] in place, slab map as
  * bd_dconv_tail.  Used by the tensor-core arm, whose TMA-fed A operand cannot be transformed on the fly. */
 int bd_gn_gelu_apply(float* h, const float* mean_rstd, const float* gamma, const float* beta, long long M, int C,

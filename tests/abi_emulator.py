@@ -176,6 +176,32 @@ def bd_dconv_tail(x, u, mr, gamma, beta, scale, M, Cc, rows_per_item, spi, strea
     xv += f32(scale, Cc) * (g[:, 0::2] * sigmoid(g[:, 1::2]))
 
 
+def _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi):
+    hv = f32(h, M * ldh).reshape(M, ldh)[:, :hid]
+    m = np.arange(M)
+    slab = (m // rpi) * spi + (m % spi)
+    st = f32(mr1, 2 * (int(slab.max()) + 1)).reshape(-1, 2)[slab]
+    g = gelu((hv - st[:, :1]) * st[:, 1:2] * f32(g1, hid) + f32(be1, hid))
+    u = g @ f32(w2t, hid * 2 * Cc).reshape(hid, 2 * Cc) + f32(b2, 2 * Cc)
+    return u.astype(np.float32), slab
+
+
+def bd_dconv_expand_stats(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, M, Cc, rpi, spi, stream):
+    u, slab = _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi)
+    st = f64(sums2, 2 * (int(slab.max()) + 1)).reshape(-1, 2)
+    u64 = u.astype(np.float64)
+    np.add.at(st[:, 0], slab, u64.sum(1))
+    np.add.at(st[:, 1], slab, (u64 ** 2).sum(1))
+
+
+def bd_dconv_expand_update(h, ldh, hid, mr1, g1, be1, w2t, b2, mr2, g2, be2, scale, x, M, Cc, rpi, spi, stream):
+    u, slab = _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi)
+    st = f32(mr2, 2 * (int(slab.max()) + 1)).reshape(-1, 2)[slab]
+    v = (u - st[:, :1]) * st[:, 1:2] * f32(g2, 2 * Cc) + f32(be2, 2 * Cc)
+    xv = f32(x, M * Cc).reshape(M, Cc)
+    xv += f32(scale, Cc) * (v[:, 0::2] * sigmoid(v[:, 1::2]))
+
+
 def bd_gn_gelu_apply(h, mr, gamma, beta, M, Cc, rows_per_item, spi, stream):
     hv = f32(h, M * Cc).reshape(M, Cc)
     m = np.arange(M)
