@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
     const float* __restrict__ be1, const float* __restrict__ w2t /*[hid][2C] interleaved*/, const float* __restrict__ b2,
     double* __restrict__ sums2, const float* __restrict__ mr2, const float* __restrict__ g2, const float* __restrict__ be2,
     const float* __restrict__ scale, float* __restrict__ x, long long M, int C, long long rows_per_item,
-    int slabs_per_item) {
+    int slabs_per_item, int chunks) {
   extern __shared__ __align__(16) float sm[];
   const int hid = HID_T > 0 ? HID_T : hid_rt;
   const int N = 2 * C;
@@ -41,50 +41,97 @@ __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
     for (int i = threadIdx.x; i < C; i += DC_THREADS) sS[i] = __ldg(scale + i);
   __syncthreads();
 
-  for (long long m = (long long)blockIdx.x * DC_THREADS + threadIdx.x; m < M; m += (long long)gridDim.x * DC_THREADS) {
+  // work item = (row, channel chunk): deep layers have few rows but wide C, so a row is split into `chunks`
+  // column ranges to keep enough threads in flight (each recomputes the row's short g vector)
+  const int ncols = N / chunks;           // interleaved columns per chunk (multiple of 4)
+  const long long items = M * chunks;
+  // running statistics of the time branch (one GroupNorm item per batch item: consecutive rows share a slab)
+  long long run_slab = -1;
+  float run_s = 0.f, run_q = 0.f;
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * DC_THREADS;
+  const long long base0 = (long long)blockIdx.x * DC_THREADS + threadIdx.x;
+  for (long long it0 = (long long)blockIdx.x * DC_THREADS; it0 < items; it0 += stride) {
+    const long long it = it0 + threadIdx.x;
+    (void)base0;
+    const bool live = it < items;
+    // chunk-major order: the lanes of a warp work on consecutive rows of the SAME column range, so the
+    // shared-memory weight reads stay warp-uniform broadcasts
+    const int chunk = live ? (int)(it / M) : 0;
+    const long long m = live ? it - (long long)chunk * M : 0;
+    const int n_lo = chunk * ncols;
     const long long slab = (m / rows_per_item) * slabs_per_item + (m % slabs_per_item);
-    const float mean1 = __ldg(mr1 + 2 * slab), rstd1 = __ldg(mr1 + 2 * slab + 1);
-    float g[HID_T > 0 ? HID_T : MAX_HID];
-    const float* hr = h + m * ldh;
-#pragma unroll
-    for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k)
-      if (k < hid) g[k] = bd_gelu(fmaf((__ldg(hr + k) - mean1) * rstd1, __ldg(g1 + k), __ldg(be1 + k)));
-    float mean2 = 0.f, rstd2 = 1.f;
-    if (FINAL) {
-      mean2 = __ldg(mr2 + 2 * slab);
-      rstd2 = __ldg(mr2 + 2 * slab + 1);
-    }
     float s = 0.f, q = 0.f;
-    float* xr = FINAL ? x + m * C : nullptr;
-    for (int n = 0; n < N; n += 4) {      // 4 interleaved columns = (value, gate) of 2 channels
-      float4 u = *reinterpret_cast<const float4*>(sB + n);
+    if (live) {
+      const float mean1 = __ldg(mr1 + 2 * slab), rstd1 = __ldg(mr1 + 2 * slab + 1);
+      float g[HID_T > 0 ? HID_T : MAX_HID];
+      const float* hr = h + m * ldh;
 #pragma unroll
-      for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k) {
-        if (k < hid) {
-          const float4 w = *reinterpret_cast<const float4*>(sW + k * N + n);
-          u.x = fmaf(w.x, g[k], u.x); u.y = fmaf(w.y, g[k], u.y);
-          u.z = fmaf(w.z, g[k], u.z); u.w = fmaf(w.w, g[k], u.w);
-        }
-      }
+      for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k)
+        if (k < hid) g[k] = bd_gelu(fmaf((__ldg(hr + k) - mean1) * rstd1, __ldg(g1 + k), __ldg(be1 + k)));
+      float mean2 = 0.f, rstd2 = 1.f;
       if (FINAL) {
-        const float4 ga = *reinterpret_cast<const float4*>(sG + n), be = *reinterpret_cast<const float4*>(sBe + n);
-        const float a0 = fmaf((u.x - mean2) * rstd2, ga.x, be.x), t0 = fmaf((u.y - mean2) * rstd2, ga.y, be.y);
-        const float a1 = fmaf((u.z - mean2) * rstd2, ga.z, be.z), t1 = fmaf((u.w - mean2) * rstd2, ga.w, be.w);
-        const float2 sc = *reinterpret_cast<const float2*>(sS + (n >> 1));
-        float2* xp = reinterpret_cast<float2*>(xr + (n >> 1));
-        float2 xv = *xp;
-        xv.x = fmaf(sc.x, a0 * bd_sigmoid(t0), xv.x);
-        xv.y = fmaf(sc.y, a1 * bd_sigmoid(t1), xv.y);
-        *xp = xv;
-      } else {
-        s += (u.x + u.y) + (u.z + u.w);
-        q = fmaf(u.x, u.x, fmaf(u.y, u.y, fmaf(u.z, u.z, fmaf(u.w, u.w, q))));
+        mean2 = __ldg(mr2 + 2 * slab);
+        rstd2 = __ldg(mr2 + 2 * slab + 1);
+      }
+      float* xr = FINAL ? x + m * C : nullptr;
+      float2 xnext = make_float2(0.f, 0.f);
+      if (FINAL) xnext = *reinterpret_cast<const float2*>(xr + (n_lo >> 1));
+      for (int n = n_lo; n < n_lo + ncols; n += 4) {   // 4 interleaved columns = (value, gate) of 2 channels
+        const float2 xv0 = xnext;                      // x of this group was requested one group ago
+        if (FINAL && n + 4 < n_lo + ncols) xnext = *reinterpret_cast<const float2*>(xr + ((n + 4) >> 1));
+        float4 u = *reinterpret_cast<const float4*>(sB + n);
+#pragma unroll
+        for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k) {
+          if (k < hid) {
+            const float4 w = *reinterpret_cast<const float4*>(sW + k * N + n);
+            u.x = fmaf(w.x, g[k], u.x); u.y = fmaf(w.y, g[k], u.y);
+            u.z = fmaf(w.z, g[k], u.z); u.w = fmaf(w.w, g[k], u.w);
+          }
+        }
+        if (FINAL) {
+          const float4 ga = *reinterpret_cast<const float4*>(sG + n), be = *reinterpret_cast<const float4*>(sBe + n);
+          const float a0 = fmaf((u.x - mean2) * rstd2, ga.x, be.x), t0 = fmaf((u.y - mean2) * rstd2, ga.y, be.y);
+          const float a1 = fmaf((u.z - mean2) * rstd2, ga.z, be.z), t1 = fmaf((u.w - mean2) * rstd2, ga.w, be.w);
+          const float2 sc = *reinterpret_cast<const float2*>(sS + (n >> 1));
+          float2 xv = xv0;
+          xv.x = fmaf(sc.x, a0 * bd_sigmoid(t0), xv.x);
+          xv.y = fmaf(sc.y, a1 * bd_sigmoid(t1), xv.y);
+          *reinterpret_cast<float2*>(xr + (n >> 1)) = xv;
+        } else {
+          s += (u.x + u.y) + (u.z + u.w);
+          q = fmaf(u.x, u.x, fmaf(u.y, u.y, fmaf(u.z, u.z, fmaf(u.w, u.w, q))));
+        }
       }
     }
     if (!FINAL) {
-      atomicAdd(&sums2[2 * slab], (double)s);
-      atomicAdd(&sums2[2 * slab + 1], (double)q);
+      // the whole warp usually sits in one slab (always, in the time branch): one atomic pair per warp and
+      // slab change instead of one per row
+      const long long slab0 = __shfl_sync(0xffffffffu, slab, 0);
+      const bool uniform = __all_sync(0xffffffffu, !live || slab == slab0);
+      if (uniform) {
+        const float ws = bd_warp_sum(s), wq = bd_warp_sum(q);
+        if (lane == 0) {
+          if (slab0 != run_slab) {
+            if (run_slab >= 0) {
+              atomicAdd(&sums2[2 * run_slab], (double)run_s);
+              atomicAdd(&sums2[2 * run_slab + 1], (double)run_q);
+            }
+            run_slab = slab0;
+            run_s = run_q = 0.f;
+          }
+          run_s += ws;
+          run_q += wq;
+        }
+      } else if (live) {
+        atomicAdd(&sums2[2 * slab], (double)s);
+        atomicAdd(&sums2[2 * slab + 1], (double)q);
+      }
     }
+  }
+  if (!FINAL && lane == 0 && run_slab >= 0) {
+    atomicAdd(&sums2[2 * run_slab], (double)run_s);
+    atomicAdd(&sums2[2 * run_slab + 1], (double)run_q);
   }
 }
 
@@ -93,7 +140,10 @@ int launch_expand(const float* h, int ldh, int hid, const float* mr1, const floa
                   const float* b2, double* sums2, const float* mr2, const float* g2, const float* be2, const float* scale,
                   float* x, long long M, int C, long long rpi, int spi, cudaStream_t st) {
   const int smem = (hid * 2 * C + 2 * C * 3 + C) * (int)sizeof(float);
-  int grid = (int)((M + DC_THREADS - 1) / DC_THREADS);
+  // split rows into channel chunks until ~256k work items exist (chunk = multiple of 2 channels)
+  int chunks = 1;
+  while (M * chunks < 262144 && chunks < 16 && (C % (4 * chunks)) == 0 && C / (2 * chunks) >= 8) chunks *= 2;
+  int grid = (int)((M * chunks + DC_THREADS - 1) / DC_THREADS);
   const int cap = 148 * (smem > 96 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 8) * 2;   // grid-stride: weights staged once per CTA
   if (grid > cap) grid = cap;
 #define BD_DC_CASE(H)                                                                                             \
@@ -105,7 +155,7 @@ int launch_expand(const float* h, int ldh, int hid, const float* mr1, const floa
       return BD_ERR_CUDA;                                                                                         \
     }                                                                                                             \
     dconv_expand_kernel<H, FINAL><<<grid, DC_THREADS, smem, st>>>(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2,  \
-                                                                  be2, scale, x, M, C, rpi, spi);                 \
+                                                                  be2, scale, x, M, C, rpi, spi, chunks);         \
     return bd_check_launch("dconv_expand_kernel");                                                                \
   }
   BD_DC_CASE(6) BD_DC_CASE(12) BD_DC_CASE(24) BD_DC_CASE(48)
@@ -116,7 +166,7 @@ int launch_expand(const float* h, int ldh, int hid, const float* mr1, const floa
     return BD_ERR_CUDA;
   }
   dconv_expand_kernel<0, FINAL><<<grid, DC_THREADS, smem, st>>>(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2, be2,
-                                                                scale, x, M, C, rpi, spi);
+                                                                scale, x, M, C, rpi, spi, chunks);
   return bd_check_launch("dconv_expand_kernel");
 }
 
