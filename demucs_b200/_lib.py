@@ -13,7 +13,7 @@ import typing as tp
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdemucs_b200.so")
-SOURCES = ["api.cu", "spectral.cu", "gemm_simt.cu", "gemm_tc.cu", "norm.cu", "dconv.cu", "attention.cu",
+SOURCES = ["api.cu", "spectral.cu", "gemm_simt.cu", "gemm_tc.cu", "norm.cu", "dconv.cu", "attention.cu", "attention_tc.cu",
            "ola.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -66,7 +66,7 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_layer_norm": [_P, _P, _P, _P, _P, _I, _LL, _I, _P],
     "bd_item_stats": [_P, _P, _I, _LL, _P],
     "bd_group_norm_apply": [_P, _P, _P, _P, _I, _LL, _I, _P],
-    "bd_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bd_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "bd_overlap_add": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _LL, _P, _F, _I, _P],
 }
 EXPORTS = ["bd_last_error", "bd_version"] + list(SIGNATURES)

@@ -27,6 +27,8 @@ int bd_conv_gemm_tc(const bd_gemm_desc* d, void* stream, int* handled);
 bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d);
 int bd_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
                       int ldk, int ldv, int ldo, void* stream);
+int bd_attention_tc(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
+                    int ldk, int ldv, int ldo, float* ws, void* stream);
 
 extern "C" {
 
@@ -51,8 +53,8 @@ int bd_conv_gemm_arm(const bd_gemm_desc* d) {
 }
 
 int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
-                 int ldk, int ldv, int ldo, int math, void* stream) {
-  (void)math;
+                 int ldk, int ldv, int ldo, int math, float* ws, void* stream) {
+  if (math == BD_MATH_TF32) return bd_attention_tc(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, ws, stream);
   return bd_attention_simt(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, stream);
 }
 

@@ -300,20 +300,21 @@ class Engine:
         W, D, H = self.W, self.cfg.transformer_dim, self.cfg.t_heads
         Win, bin_ = W[f"{p}.{attn}.in_proj_weight"], W[f"{p}.{attn}.in_proj_bias"]
         att = self._buf(key, f"att{tag}", B * Tq * D)
+        ws = self._buf(key, f"att_ws{tag}", B * D * ((Tk + 3) // 4 * 4)) if self.mode == "tf32" else None
         if kv_src is None:  # self attention: one packed projection
             qkv = self._buf(key, f"qkv{tag}", B * Tq * 3 * D)
             self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv)
             self._k("bd_attention", ptr(qkv), qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, ptr(att),
-                    B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), self._stream(),
-                    flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label="attention")
+                    B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), ptr(ws), self._stream(),
+                    flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label="attention_tc" if self.mode == "tf32" else "attention_simt")
         else:
             q = self._buf(key, f"q{tag}", B * Tq * D)
             kv = self._buf(key, f"kv{tag}", B * Tk * 2 * D)
             self._gemm(M=B * Tq, N=D, Cin=D, x=x, w=Win[:D], bias=bin_[:D], out=q)
             self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv)
             self._k("bd_attention", ptr(q), ptr(kv), kv.data_ptr() + 4 * D, ptr(att),
-                    B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), self._stream(),
-                    flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label="attention")
+                    B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), ptr(ws), self._stream(),
+                    flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label="attention_tc" if self.mode == "tf32" else "attention_simt")
         return att
 
     def _math(self) -> int:

@@ -231,7 +231,7 @@ def _strided(p, B, T, ld, ncol):
     return np.lib.stride_tricks.as_strided(a, shape=(B, T, ncol), strides=(T * ld * 4, ld * 4, 4))
 
 
-def bd_attention(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, math_, stream):
+def bd_attention(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, math_, ws, stream):
     D = 64 * H
     qv, kv, vv = _strided(q, B, Tq, ldq, D), _strided(k, B, Tk, ldk, D), _strided(v, B, Tk, ldv, D)
     ov = _strided(o, B, Tq, ldo, D)
