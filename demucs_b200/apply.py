@@ -201,6 +201,11 @@ def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor,
     key = ("apply", rows, valid)
     segs = eng._buf(key, "segs", max(n_local, 1) * rows * valid).view(max(n_local, 1), rows, valid)
     parent = TensorChunk(track, ps.offset0, ps.length)
+    if model.cfg.t_layers > 0:
+        # the reference draws random.randrange(1) inside every segment forward (transformer.py:680); every
+        # rank draws for ALL segments so that sharded ranks keep identical RNG streams
+        for _ in range(nseg):
+            random.randrange(1)
     for s0 in range(lo_seg, hi_seg, batch_size):
         idx = list(range(s0, min(s0 + batch_size, hi_seg)))
         batch = eng._buf(key, "batch", len(idx) * B * Cc * valid).view(len(idx) * B, Cc, valid)
@@ -209,8 +214,6 @@ def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor,
             lo, hi, left, _ = TensorChunk(parent, offsets[i], seg_len).window(valid)
             batch[j * B:(j + 1) * B, :, left:left + hi - lo].copy_(track[..., lo:hi])
         for i in idx:
-            if model.cfg.t_layers > 0:
-                random.randrange(1)  # the reference's per-forward RNG draw (transformer.py:680)
             if notify:
                 notify(offsets[i], "start")
         res = eng.forward(batch)                                   # [n*B, S, C, valid]
