@@ -272,7 +272,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("BD_MODE", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--mode", default=os.environ.get("BD_MODE", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--batch", type=int, default=16, help="segments per forward")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
