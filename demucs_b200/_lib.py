@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 BD_MAX_TAPS = 9
 A_NONE, A_GN_GELU, A_ITEM_AFFINE = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_GLU = 0, 1, 2
-MATH_FP32, MATH_TF32 = 0, 1
+MATH_FP32, MATH_TF32, MATH_TF32X3 = 0, 1, 2
 
 
 class KernelError(RuntimeError):

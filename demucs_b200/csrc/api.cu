@@ -40,7 +40,7 @@ int bd_conv_gemm(const bd_gemm_desc* d, void* stream) {
     bd_set_error("bd_conv_gemm: null descriptor");
     return BD_ERR_ARG;
   }
-  if (d->math == BD_MATH_TF32) {
+  if (d->math == BD_MATH_TF32 || d->math == BD_MATH_TF32X3) {
     int handled = 0;
     int rc = bd_conv_gemm_tc(d, stream, &handled);
     if (rc != BD_OK || handled) return rc;
@@ -49,7 +49,7 @@ int bd_conv_gemm(const bd_gemm_desc* d, void* stream) {
 }
 
 int bd_conv_gemm_arm(const bd_gemm_desc* d) {
-  return (d && d->math == BD_MATH_TF32 && bd_conv_gemm_tc_eligible(*d)) ? 1 : 0;
+  return (d && (d->math == BD_MATH_TF32 || d->math == BD_MATH_TF32X3) && bd_conv_gemm_tc_eligible(*d)) ? 1 : 0;
 }
 
 int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,

@@ -36,13 +36,16 @@ constexpr int kThreads = 192;
 
 // TBK floats per k-block: 32 -> 128B swizzle, 16 -> 64B swizzle.  TBN = tile columns = UMMA N (16..128):
 // narrow outputs (DConv hidden widths, last-layer channels) get narrow tiles instead of zero padding.
-template <int TBK, int TBN>
+// X3: error-compensated "3xTF32": every operand tile is split in shared memory into hi = rn_tf32(x) and
+// lo = x - hi and the product is accumulated as hi*hi + lo*hi + hi*lo (fp32-class accuracy, 3x the MMAs).
+template <int TBK, int TBN, bool X3>
 struct Cfg {
-  static constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
-  static constexpr int kStagesRaw = 98304 / (kStageBytesA + kStageBytesB);   // ~96 KB: two CTAs per SM
+  static constexpr int kTileBytesA = TBM * TBK * 4, kTileBytesB = TBN * TBK * 4;
+  static constexpr int kStageBytesA = kTileBytesA * (X3 ? 2 : 1), kStageBytesB = kTileBytesB * (X3 ? 2 : 1);
+  static constexpr int kStagesRaw = (X3 ? 196608 : 98304) / (kStageBytesA + kStageBytesB);   // 96 KB: 2 CTAs / SM
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kStagingBytes = 4 * 32 * (TBN + 4) * 4;
-  static constexpr int kTailBytes = 256 /*barriers*/ + 128 * 32 /*RowInfo*/;
+  static constexpr int kTailBytes = 512 /*barriers*/ + 128 * 32 /*RowInfo*/;
   static constexpr int smem_bytes(int stages) {
     int pipe = stages * (kStageBytesA + kStageBytesB);
     return (pipe > kStagingBytes ? pipe : kStagingBytes) + 1024 /*align slack*/ + kTailBytes;
@@ -73,6 +76,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -168,6 +174,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// round-to-nearest TF32 (low 13 mantissa bits cleared): exactly representable, so the tensor core's own
+// fp32 -> tf32 conversion of it is the identity
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -179,12 +193,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 
 // ---- kernel -------------------------------------------------------------------------------------------
-template <int TBK, int TBN>
+template <int TBK, int TBN, bool X3>
 __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const bd_gemm_desc d, const TileGeom g) {
-  using C_ = Cfg<TBK, TBN>;
+  using C_ = Cfg<TBK, TBN, X3>;
   constexpr int kStages = C_::kStages, kStageBytesA = C_::kStageBytesA, kStageBytesB = C_::kStageBytesB;
+  constexpr int kTileBytesA = C_::kTileBytesA, kTileBytesB = C_::kTileBytesB;
   constexpr int kTmemCols = C_::kTmemCols;
   constexpr int CW = TBN < 32 ? TBN : 32;            // columns per TMEM load
   extern __shared__ uint8_t smem_raw[];
@@ -197,7 +212,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (pipe_bytes > kStagingBytes ? pipe_bytes : kStagingBytes));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* conv_bar = tmem_full_bar + 1;            // [kStages] X3: hi/lo tiles written by the converter warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kStages);
   __shared__ double red[8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,6 +230,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 128);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -236,7 +253,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
         const int s = kb % nstages;
         const uint32_t ph = (kb / nstages) & 1;
         mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
+        mbar_expect_tx(&full_bar[s], kTileBytesA + kTileBytesB);
         // A: the tap-shifted window of the activation tensor; out-of-range rows/positions read as zero
         tma_load_4d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, i0s + d.d0[tap], i1s + d.d1[tap], b);
         tma_load_2d(&map_b, &full_bar[s], sB + s * kStageBytesB, tap * d.Cin + cb * TBK, n0);
@@ -253,13 +270,22 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % nstages;
         const uint32_t ph = (kb / nstages) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], ph);
         tcgen05_fence_after();
         const uint64_t adesc = make_kmajor_desc<TBK>(sA + s * kStageBytesA);
         const uint64_t bdesc = make_kmajor_desc<TBK>(sB + s * kStageBytesB);
 #pragma unroll
-        for (int k = 0; k < TBK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B: advance the start address by 32 B >> 4
-          umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < TBK / 8; ++k) {   // UMMA_K = 8 tf32 = 32 B: advance the start address by 32 B >> 4
+          if constexpr (X3) {
+            const uint64_t alo = make_kmajor_desc<TBK>(sA + s * kStageBytesA + kTileBytesA);
+            const uint64_t blo = make_kmajor_desc<TBK>(sB + s * kStageBytesB + kTileBytesB);
+            umma_tf32(tmem_base, alo + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);   // small terms first
+            umma_tf32(tmem_base, adesc + 2 * k, blo + 2 * k, idesc, 1);
+            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+        }
         tcgen05_commit(&empty_bar[s]);      // frees the smem stage once these MMAs have read it
       }
       tcgen05_commit(tmem_full_bar);        // accumulator complete
@@ -274,6 +300,28 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     const int i0 = i0s + (r & (g.R0 - 1)), i1 = i1s + (r >> g.log2R0);
     const bool row_ok = i0 < d.I0 && i1 < d.I1;
     const long long m = ((long long)b * d.I1 + i1) * d.I0 + i0;
+    if constexpr (X3) {
+      // ===== operand splitter: these 4 warps are idle during the main loop =====
+      const int et = threadIdx.x - 64;      // 0..127
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % nstages;
+        mbar_wait(&full_bar[s], (kb / nstages) & 1);
+        auto split = [&](uint8_t* base, int tile_bytes) {
+          float4* hi = reinterpret_cast<float4*>(base);
+          float4* lo = reinterpret_cast<float4*>(base + tile_bytes);
+          for (int i = et; i < tile_bytes / 16; i += 128) {
+            const float4 x = hi[i];
+            const float4 h = make_float4(rn_tf32(x.x), rn_tf32(x.y), rn_tf32(x.z), rn_tf32(x.w));
+            hi[i] = h;
+            lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          }
+        };
+        split(sA + s * kStageBytesA, kTileBytesA);
+        split(sB + s * kStageBytesB, kTileBytesB);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> UMMA reads
+        mbar_arrive(&conv_bar[s]);
+      }
+    }
     mbar_wait_relaxed(tmem_full_bar, 0);    // also: every MMA has finished reading the smem stages
     tcgen05_fence_after();
     EpiRow er;
@@ -437,9 +485,9 @@ int pow2_ceil(int v) {
   return p;
 }
 
-template <int TBK, int TBN>
+template <int TBK, int TBN, bool X3>
 int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st) {
-  using C_ = Cfg<TBK, TBN>;
+  using C_ = Cfg<TBK, TBN, X3>;
   alignas(64) CUtensorMap map_a, map_b;
   // activations: (c, j0, j1, item); size-1 axes get a harmless contiguous stride
   const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
@@ -456,7 +504,7 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<TBK, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<TBK, TBN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C_::kSmemBytes);
     if (e != cudaSuccess) {
       bd_set_error("bd_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -468,7 +516,7 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
   TileGeom gg = g;
   const int nkb = d.taps * g.cpb;
   gg.stages = nkb < C_::kStages ? nkb : C_::kStages;
-  conv_gemm_tc_kernel<TBK, TBN><<<grid, kThreads, C_::smem_bytes(gg.stages), st>>>(map_a, map_b, d, gg);
+  conv_gemm_tc_kernel<TBK, TBN, X3><<<grid, kThreads, C_::smem_bytes(gg.stages), st>>>(map_a, map_b, d, gg);
   return bd_check_launch("conv_gemm_tc_kernel");
 }
 
@@ -502,13 +550,16 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
   const cudaStream_t st = (cudaStream_t)stream;
 #define BD_TC_CASE(K_, N_) \
-  if (tbn == N_) rc = launch_tc<K_, N_>(d, g, items, st); else
+  if (tbn == N_) rc = x3 ? launch_tc<K_, N_, true>(d, g, items, st) : launch_tc<K_, N_, false>(d, g, items, st); else
+  const bool x3 = d.math == BD_MATH_TF32X3;
   if (d.Cin % 32 == 0) {
     g.cpb = d.Cin / 32;
-    BD_TC_CASE(32, 16) BD_TC_CASE(32, 32) BD_TC_CASE(32, 64) rc = launch_tc<32, 128>(d, g, items, st);
+    BD_TC_CASE(32, 16) BD_TC_CASE(32, 32) BD_TC_CASE(32, 64)
+    rc = x3 ? launch_tc<32, 128, true>(d, g, items, st) : launch_tc<32, 128, false>(d, g, items, st);
   } else {
     g.cpb = d.Cin / 16;
-    BD_TC_CASE(16, 16) BD_TC_CASE(16, 32) BD_TC_CASE(16, 64) rc = launch_tc<16, 128>(d, g, items, st);
+    BD_TC_CASE(16, 16) BD_TC_CASE(16, 32) BD_TC_CASE(16, 64)
+    rc = x3 ? launch_tc<16, 128, true>(d, g, items, st) : launch_tc<16, 128, false>(d, g, items, st);
   }
 #undef BD_TC_CASE
   *handled = 1;

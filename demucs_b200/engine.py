@@ -26,7 +26,7 @@ from ._lib import GemmDesc, call, ptr
 from .config import HTDemucsConfig
 from .weights import check_state_dict
 
-MODES = ("fp32", "tf32")
+MODES = ("fp32", "tf32", "tf32x3")
 
 
 def _interleave_glu(w: torch.Tensor) -> torch.Tensor:
@@ -175,7 +175,7 @@ class Engine:
         if self.device.type != "cuda" and _lib.TEST_HOOK is None:
             raise _lib.KernelError("demucs_b200 runs on CUDA devices only (there is no CPU path)")
         _lib.lib()  # fail loudly now if the extension is missing
-        self.W = PackedWeights(cfg, state, self.device, tc_forms=(mode == "tf32"))
+        self.W = PackedWeights(cfg, state, self.device, tc_forms=(mode != "fp32"))
         self.window = torch.hann_window(cfg.nfft, periodic=True, dtype=torch.float32).to(self.device)
         k = np.arange(cfg.nfft, dtype=np.float64)
         tw = np.stack([np.cos(2 * np.pi * k / cfg.nfft), -np.sin(2 * np.pi * k / cfg.nfft)], axis=1)
@@ -236,13 +236,14 @@ class Engine:
         d.out, d.convt, d.O0 = ptr(out), convt, O0
         d.stats_out = ptr(stats_out)
         d.stat_div, d.stat_mul, d.stat_mod = stat
-        d.math = _lib.MATH_TF32 if (self.mode == "tf32" and tc) else _lib.MATH_FP32
+        d.math = _lib.MATH_FP32 if (self.mode == "fp32" or not tc) else \
+            (_lib.MATH_TF32 if self.mode == "tf32" else _lib.MATH_TF32X3)
         K = len(taps) * Cin
         rows_in = (M // (I1 * I0)) * d.J1 * d.J0          # input positions (each read once, algorithmically)
         nbytes = 4.0 * (rows_in * Cin + N * K + (M * (N if convt else n_out) if out is not None else 0))
         nbytes += 4.0 * M * n_out * ((resid is not None) + (addend is not None))
         arm = "simt"
-        if d.math == _lib.MATH_TF32 and _lib.TEST_HOOK is None:
+        if d.math != _lib.MATH_FP32 and _lib.TEST_HOOK is None:
             arm = "tc" if _lib.lib().bd_conv_gemm_arm(C.byref(d)) else "simt"
         tile = 128 if N > 64 else 64 if N > 32 else 32 if (N > 16 or act == _lib.ACT_GLU) else 16
         self._k("bd_conv_gemm", C.byref(d), self._stream(), flops=2.0 * M * N * K, nbytes=nbytes,
@@ -259,7 +260,7 @@ class Engine:
         M = B * T * Fr
         slabs = B * Fr
         stat = (T * Fr, Fr, Fr)                      # slab(m) = b*Fr + fr
-        tc = self.mode == "tf32"
+        tc = self.mode != "fp32"
         hp = (hid + 15) // 16 * 16 if tc else hid      # tensor-core arm: h is stored 16-column padded
         h = self._buf(key, f"dconv_h{tag}", M * hp)
         sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64)
@@ -318,6 +319,8 @@ class Engine:
         return att
 
     def _math(self) -> int:
+        """Arithmetic of the attention core: tcgen05 in "tf32" mode, exact fp32 otherwise (the
+        error-compensated mode keeps the softmax path in fp32)."""
         return _lib.MATH_TF32 if self.mode == "tf32" else _lib.MATH_FP32
 
     def _ln(self, x, y, p: str, M: int, pos=None, period=0):
@@ -516,7 +519,7 @@ class Engine:
                 self._dconv(key, f"decoder.{j}", y, B, T, Fcur, Cc, "_f")
             # ConvTranspose2d(k=(8,1), s=(4,1)) + crop [2:-2] + GELU (+ next skip) (hdemucs.py:326-334)
             nxt = self._buf(key, names[(j + 1) % 2], dec_f_numel)[: B * T * 4 * Fcur * Cout]
-            three = self.mode == "tf32" and 4 * Cout >= 64   # tensor-core form: no halo row
+            three = self.mode != "fp32" and 4 * Cout >= 64   # tensor-core form: no halo row
             self._gemm(M=B * T * (Fcur + (0 if three else 1)), N=4 * Cout, Cin=Cc, x=y,
                        w=W[f"decoder.{j}.conv_tr.w3" if three else f"decoder.{j}.conv_tr.w"],
                        bias=W[f"decoder.{j}.conv_tr.b"], out=nxt,
@@ -537,7 +540,7 @@ class Engine:
             if cfg.dconv_mode & 2:
                 self._dconv(key, f"tdecoder.{j}", y, B, Tin, 1, Cc, "_t")
             nxt = self._buf(key, "dec_tb" if (j % 2 == 0) else "dec_ta", dec_t_numel)[: B * Tout * Cout_t]
-            three = self.mode == "tf32" and 4 * Cout_t >= 64
+            three = self.mode != "fp32" and 4 * Cout_t >= 64
             self._gemm(M=B * (Tin + (0 if three else 1)), N=4 * Cout_t, Cin=Cc, x=y,
                        w=W[f"tdecoder.{j}.conv_tr.w3" if three else f"tdecoder.{j}.conv_tr.w"],
                        bias=W[f"tdecoder.{j}.conv_tr.b"], out=nxt,

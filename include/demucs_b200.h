@@ -28,7 +28,9 @@ enum { BD_A_NONE = 0, BD_A_GN_GELU = 1, BD_A_ITEM_AFFINE = 2 };
 /* Epilogue activations. BD_ACT_GLU expects interleaved (value, gate) output columns. */
 enum { BD_ACT_NONE = 0, BD_ACT_GELU = 1, BD_ACT_GLU = 2 };
 /* Arithmetic of the contraction. */
-enum { BD_MATH_FP32 = 0, BD_MATH_TF32 = 1 };
+/* FP32: CUDA-core FFMA.  TF32: tcgen05 kind::tf32, single pass.  TF32X3: tcgen05, operands split into
+ * hi + lo TF32 parts in shared memory, hi*hi + lo*hi + hi*lo (fp32-class accuracy). */
+enum { BD_MATH_FP32 = 0, BD_MATH_TF32 = 1, BD_MATH_TF32X3 = 2 };
 
 /* One convolution / linear layer expressed as an implicit GEMM
  *   out[m, n] = epilogue( sum_{tap, ci} A(m, tap, ci) * w[n, tap*Cin + ci] + bias[n] )

@@ -250,3 +250,28 @@ def test_forward_blocks_small_tf32_mode():
     print("small tf32 taps", {k: f"{e:.1e}" for k, e in errs.items()})
     assert max(errs.values()) < FAST_TOL
     assert max(stem_errors(got.cpu(), want)) < FAST_TOL
+
+
+@pytest.mark.parametrize("name", ["htdemucs_default.npz", "htdemucs_ls05.npz"])
+def test_forward_htdemucs_tf32x3_mode(name):
+    """Error-compensated tensor-core mode (hi*hi + lo*hi + hi*lo on tcgen05, fp32 softmax path): the
+    north_star's fp32/TF32 bound, per-stem relative L2 <= 1e-4, on both weight fixtures."""
+    g = golden(name)
+    cfg = htdemucs_config()
+    W, mix = forward_fixture_inputs(g, cfg)
+    eng = Engine(cfg, W, DEV, mode="tf32x3")
+    taps = {}
+    got = eng.forward(mix.to(DEV), taps)
+    torch.cuda.synchronize()
+    errs = {}
+    for key in g.files:
+        if key.startswith("tap."):
+            errs[key[4:]] = rel_l2(strided(taps[key[4:]].contiguous(), int(g["tap_stride"])), g[key])
+    e_out = rel_l2(strided(got, int(g["stride"])), g["out"])
+    print(name, "tf32x3 out rel-L2", e_out, "worst tap", max(errs.items(), key=lambda kv: kv[1]))
+    assert max(errs.values()) < 1e-4
+    with torch.no_grad():
+        want = htdemucs_forward(W, cfg, mix)
+    stems = stem_errors(got.cpu(), want)
+    print("per-stem", stems)
+    assert max(stems) < STEM_TOL

@@ -14,7 +14,7 @@ import demucs_b200 as D
 from demucs_b200.engine import Engine
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
 def test_engine_forward_matches_oracle_and_golden(mode):
     """Both descriptor forms (the tf32 mode uses the 3-tap transposed-conv packing)."""
     g = golden("small_short.npz")
