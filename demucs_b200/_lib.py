@@ -44,7 +44,7 @@ class GemmDesc(C.Structure):
         ("act", C.c_int), ("rowbias", C.c_void_p), ("rowbias_period", C.c_int),
         ("resid", C.c_void_p), ("scale", C.c_void_p), ("addend", C.c_void_p),
         ("out", C.c_void_p), ("os_b", C.c_longlong), ("os_1", C.c_longlong), ("os_0", C.c_longlong),
-        ("convt", C.c_int), ("O0", C.c_int),
+        ("convt", C.c_int), ("O0", C.c_int), ("oc_split", C.c_int), ("oc_stride", C.c_longlong),
         ("stats_out", C.c_void_p), ("stat_div", C.c_int), ("stat_mul", C.c_int), ("stat_mod", C.c_int),
         ("math", C.c_int),
     ]
@@ -55,6 +55,7 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_stft_cac": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "bd_finalize_item_norm": [_P, _P, _I, _D, _D, _P],
     "bd_istft_frames": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "bd_istft_ola": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "bd_ola_combine": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "bd_conv_gemm": [C.POINTER(GemmDesc), _P],
     "bd_conv_gemm_arm": [C.POINTER(GemmDesc)],

@@ -44,8 +44,16 @@ __device__ __forceinline__ bool bd_epi_vec_ok(const bd_gemm_desc& d) {
   ok = ok && al16(d.out) && al16(d.bias) && al16(d.rowbias) && al16(d.resid) && al16(d.scale) && al16(d.addend) &&
        al16(d.e_gamma) && al16(d.e_beta);
   if (d.convt) ok = ok && ((d.N >> 2) % 4 == 0);
+  if (d.oc_split) ok = ok && d.oc_split % 4 == 0 && d.oc_stride % 4 == 0 && d.act != BD_ACT_GLU;
   if (d.act != BD_ACT_GLU && d.rowbias) ok = ok && (d.N % 4 == 0);
   return ok;
+}
+
+// offset of output column `no` inside a row (optionally split into channel-group planes)
+__device__ __forceinline__ long long bd_col_ofs(const bd_gemm_desc& d, int no) {
+  if (d.oc_split == 0) return no;
+  const int g = no / d.oc_split;
+  return (long long)g * d.oc_stride + (no - g * d.oc_split);
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -66,7 +74,7 @@ __device__ __forceinline__ EpiMem bd_epi_fetch4(const bd_gemm_desc& d, const Epi
   if (d.act == BD_ACT_GLU) {
     e.no = n >> 1;
     const int Nout = d.N >> 1;
-    e.o = r.obase + (long long)r.i0 * d.os_0 + e.no;
+    e.o = r.obase + (long long)r.i0 * d.os_0 + bd_col_ofs(d, e.no);
     if (d.rowbias) { const float2 t = ldg2(d.rowbias + (size_t)r.rb_row * Nout + e.no); e.rowbias.x = t.x; e.rowbias.y = t.y; }
     if (d.resid) { const float2 t = ldg2(d.resid + e.o); e.resid.x = t.x; e.resid.y = t.y; }
     if (d.addend) { const float2 t = ldg2(d.addend + e.o); e.addend.x = t.x; e.addend.y = t.y; }
@@ -84,9 +92,9 @@ __device__ __forceinline__ EpiMem bd_epi_fetch4(const bd_gemm_desc& d, const Epi
     }
     e.no = n - rr * Cout;
     Nout = Cout;
-    e.o = r.obase + (long long)o0 * d.os_0 + e.no;
+    e.o = r.obase + (long long)o0 * d.os_0 + bd_col_ofs(d, e.no);
   } else {
-    e.o = r.obase + (long long)r.i0 * d.os_0 + e.no;
+    e.o = r.obase + (long long)r.i0 * d.os_0 + bd_col_ofs(d, e.no);
   }
   if (d.rowbias) e.rowbias = ldg4(d.rowbias + (size_t)r.rb_row * Nout + e.no);
   if (d.resid) e.resid = ldg4(d.resid + e.o);
@@ -191,9 +199,9 @@ __device__ __forceinline__ bool bd_epi_apply(const bd_gemm_desc& d, const EpiRow
     if (o0 < 0 || o0 >= d.O0) return false;
     no = n - rr * Cout;
     Nout = Cout;
-    o = r.obase + (long long)o0 * d.os_0 + no;
+    o = r.obase + (long long)o0 * d.os_0 + bd_col_ofs(d, no);
   } else {
-    o = r.obase + (long long)r.i0 * d.os_0 + no;
+    o = r.obase + (long long)r.i0 * d.os_0 + bd_col_ofs(d, no);
   }
   if (d.rowbias) v += __ldg(d.rowbias + (size_t)r.rb_row * Nout + no);
   if (d.resid) v = fmaf(d.scale ? __ldg(d.scale + no) : 1.f, v, __ldg(d.resid + o));

@@ -233,6 +233,88 @@ __global__ void ola_combine_kernel(const float* __restrict__ frames, const float
   }
 }
 
+// K2 fused: spec [B, T, S, 2048, 4] (source-major, written that way by the last decoder layer) ->
+// out [B, S, 2, Lout].  One CTA owns NH consecutive hop blocks of one (item, source): it walks the NH + 3
+// frames that touch them, inverse-transforms each (two channels per complex FFT), and overlap-adds into a
+// 4096-sample ring in shared memory; a hop block leaves the SM exactly once, already cropped, with the
+// time-branch output and the de-normalisation folded in.  No frames buffer in HBM: the algorithmic traffic
+// (spectrogram in, waveform out) is the only traffic, bar the 3 recomputed halo frames per chunk.
+constexpr int NH = 24;
+
+__global__ void __launch_bounds__(NTHR) istft_ola_kernel(const float* __restrict__ spec, const float* __restrict__ norm,
+                                                         const float* __restrict__ win, const float2* __restrict__ tw,
+                                                         const float* __restrict__ xt, float* __restrict__ out, int S,
+                                                         int T, int Lseg, int Lout) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sre = dsm;
+  float* sim = sre + SPAD;
+  float* ring0 = sim + SPAD;
+  float* ring1 = ring0 + NFFT;
+  const int h0 = blockIdx.x * NH, s = blockIdx.y, b = blockIdx.z, j = threadIdx.x;
+  const float mean = norm[b * 8 + 0], sd = norm[b * 8 + 1];
+  const float meant = norm[b * 8 + 4], stdt = norm[b * 8 + 5];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    ring0[j + r * NTHR] = 0.f;
+    ring1[j + r * NTHR] = 0.f;
+  }
+  const int h_end = min(h0 + NH, T + 2);           // hop blocks [h0, h_end)
+  for (int t = h0 - 3; t < h_end; ++t) {
+    if (t >= 0 && t < T) {
+      const float4* in = reinterpret_cast<const float4*>(spec) + (((size_t)b * T + t) * S + s) * 2048;
+      float2 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int f = j + r * NTHR;
+        if (f == 2048) {
+          v[r] = make_float2(0.f, 0.f);
+          continue;
+        }
+        const bool mirror = f > 2048;
+        const int g = mirror ? NFFT - f : f;
+        float4 q = __ldg(in + g);
+        q.x = fmaf(q.x, sd, mean); q.y = fmaf(q.y, sd, mean);
+        q.z = fmaf(q.z, sd, mean); q.w = fmaf(q.w, sd, mean);
+        if (g == 0) { q.y = 0.f; q.w = 0.f; }
+        v[r] = mirror ? make_float2(q.x + q.w, q.z - q.y) : make_float2(q.x - q.w, q.y + q.z);
+      }
+      fft4096<1>(v, sre, sim, tw);                 // ends with a __syncthreads
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int n = j + r * NTHR;
+        const float w = __ldg(win + n) * (1.0f / 64.0f / 1.5f);
+        const int p = sidx(n);
+        const int ri = (t * 1024 + n) & (NFFT - 1);   // each thread owns its ring slots: no races
+        ring0[ri] += sre[p] * w;
+        ring1[ri] += sim[p] * w;
+      }
+    }
+    __syncthreads();
+    if (t >= h0) {                                 // hop block t has now received frames t-3 .. t
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = j + r * NTHR;
+        const int ri = (t * 1024 + i) & (NFFT - 1);
+        const int n = t * 1024 + i - 1536;
+        const float a0 = ring0[ri], a1 = ring1[ri];
+        ring0[ri] = 0.f;
+        ring1[ri] = 0.f;
+        if (n >= 0 && n < Lout) {
+          float t0 = 0.f, t1 = 0.f;
+          if (xt) {
+            const float2 x2 = __ldg(reinterpret_cast<const float2*>(xt + ((size_t)b * Lseg + n) * 2 * S + 2 * s));
+            t0 = fmaf(x2.x, stdt, meant);
+            t1 = fmaf(x2.y, stdt, meant);
+          }
+          out[(((size_t)b * S + s) * 2 + 0) * Lout + n] = a0 + t0;
+          out[(((size_t)b * S + s) * 2 + 1) * Lout + n] = a1 + t1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -258,6 +340,20 @@ int bd_istft_frames(const float* spec, const float* norm, const float* window, c
   istft_frames_kernel<<<dim3(T, B), NTHR, 0, (cudaStream_t)stream>>>(spec, norm, window, (const float2*)twiddle, frames,
                                                                     S, T);
   return bd_check_launch("istft_frames_kernel");
+}
+
+int bd_istft_ola(const float* spec, const float* norm, const float* window, const float* twiddle, const float* xt,
+                 float* out, int B, int S, int T, int Lseg, int Lout, void* stream) {
+  BD_REQUIRE(B > 0 && S > 0 && T > 0 && Lout > 0 && Lout <= Lseg, "bd_istft_ola: bad sizes");
+  constexpr int smem = (2 * SPAD + 2 * NFFT) * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    bd_set_error("bd_istft_ola: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return BD_ERR_CUDA;
+  }
+  istft_ola_kernel<<<dim3((T + 2 + NH - 1) / NH, S, B), NTHR, smem, (cudaStream_t)stream>>>(
+      spec, norm, window, (const float2*)twiddle, xt, out, S, T, Lseg, Lout);
+  return bd_check_launch("istft_ola_kernel");
 }
 
 int bd_ola_combine(const float* frames, const float* xt, const float* norm, float* out, int B, int S, int T, int Lseg,

@@ -217,7 +217,7 @@ class Engine:
               xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
               a_stats_stride=0, a_gamma=None, a_beta=None, act=_lib.ACT_NONE, rowbias=None, rowbias_period=0,
               resid=None, scale=None, addend=None, convt=0, O0=0, stats_out=None, stat=(0, 0, 0),
-              e_stats=None, e_gamma=None, e_beta=None, tc=True) -> None:
+              e_stats=None, e_gamma=None, e_beta=None, oc_split=0, oc_stride=0, tc=True) -> None:
         d = GemmDesc()
         I0 = M if I0 is None else I0
         d.M, d.N, d.K, d.Cin, d.taps = M, N, len(taps) * Cin, Cin, len(taps)
@@ -234,6 +234,7 @@ class Engine:
         d.act, d.rowbias, d.rowbias_period = act, ptr(rowbias), rowbias_period
         d.resid, d.scale, d.addend = ptr(resid), ptr(scale), ptr(addend)
         d.out, d.convt, d.O0 = ptr(out), convt, O0
+        d.oc_split, d.oc_stride = oc_split, oc_stride
         d.stats_out = ptr(stats_out)
         d.stat_div, d.stat_mul, d.stat_mod = stat
         d.math = _lib.MATH_FP32 if (self.mode == "fp32" or not tc) else \
@@ -525,10 +526,16 @@ class Engine:
                        bias=W[f"decoder.{j}.conv_tr.b"], out=nxt,
                        taps=((0, -1), (0, 0), (0, 1)) if three else ((0, 0), (0, -1)), I1=T,
                        I0=Fcur + (0 if three else 1), J1=T, J0=Fcur, xs=(T * Fcur * Cc, Fcur * Cc, Cc, 1),
-                       os_=(T * 4 * Fcur * Cout, 4 * Fcur * Cout, Cout), convt=2 if three else 1, O0=4 * Fcur,
+                       # the last layer writes source-major [B, T, S, F, 4] so that an iSTFT frame is contiguous
+                       os_=(T * 4 * Fcur * Cout, 4 * Fcur * Cout, 4 if last else Cout),
+                       oc_split=4 if last else 0, oc_stride=4 * Fcur * 4 if last else 0,
+                       convt=2 if three else 1, O0=4 * Fcur,
                        act=_lib.ACT_NONE if last else _lib.ACT_GELU, addend=skip)
             if taps is not None:
-                tap(f"dec{j}", (nxt - skip if skip is not None else nxt).view(B, T, 4 * Fcur, Cout), "f")
+                if last:   # [B,T,S,F,4] -> [B,T,F,(s j)]
+                    tap(f"dec{j}", nxt.view(B, T, S, 4 * Fcur, 4).permute(0, 1, 3, 2, 4).reshape(B, T, 4 * Fcur, Cout), "f")
+                else:
+                    tap(f"dec{j}", (nxt - skip).view(B, T, 4 * Fcur, Cout), "f")
             xd, Fcur = nxt, 4 * Fcur
 
             # time: k=3 rewrite + GLU, DConv, ConvTranspose1d(k=8,s=4) + crop [2:2+length] + GELU
@@ -552,20 +559,15 @@ class Engine:
                 tap(f"tdec{j}", (nxt - skip_t if skip_t is not None else nxt).view(B, Tout, Cout_t), "t")
             xtd = nxt
 
-        # ---- K2: de-normalise, iSTFT, overlap-add, add the time branch ---------------------------------
-        frames = self._buf(key, "frames", B * S * 2 * T * 4096)
+        # ---- K2: de-normalise, iSTFT, overlap-add in shared memory, crop, add the time branch ------------
         out = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
-        self._k("bd_istft_frames", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), ptr(frames), B, S, T, st,
-                nbytes=4.0 * B * T * S * (2048 * 4 + 2 * 4096), flops=2.5 * 4096 * 12 * 2 * S * B * T)
-        self._k("bd_ola_combine", ptr(frames), ptr(xtd), ptr(norm), ptr(out), B, S, T, L, L0, st,
-                nbytes=4.0 * B * S * 2 * (T * 4096 + L + L0))
+        self._k("bd_istft_ola", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), ptr(xtd), ptr(out),
+                B, S, T, L, L0, st, nbytes=4.0 * B * S * (T * 2048 * 4 + 2 * L + 2 * L0),
+                flops=2.5 * 4096 * 12 * 2 * S * B * T)
         if taps is not None:
-            zero_t = torch.zeros_like(xtd)
-            nrm0 = norm.clone()
-            nrm0[4::8] = 0
-            nrm0[5::8] = 0
             only = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
-            self._k("bd_ola_combine", ptr(frames), ptr(zero_t), ptr(nrm0), ptr(only), B, S, T, L, L0, st)
+            self._k("bd_istft_ola", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), None, ptr(only),
+                    B, S, T, L, L0, st)
             taps["istft"] = only
             taps["time_out"] = out - only
         return out

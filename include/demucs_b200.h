@@ -76,6 +76,9 @@ typedef struct bd_gemm_desc {
                           1: rows = input positions + 1, taps (0,-1): o0 = 4*i0 + r - 2
                           2: rows = input positions, taps (-1,0,+1), zero-extended weights: o0 = 4*i0 + r */
   int O0;              /* convt: valid output positions are 0 <= o0 < O0 */
+  int oc_split;        /* 0: output column c lands at + c.  > 0 (multiple of 4): at + (c / oc_split)*oc_stride +
+                          c % oc_split -- writes channel groups (e.g. the 4 floats of one source) to separate planes */
+  long long oc_stride;
   double* stats_out;   /* [slab][2] += (sum, sumsq) of stored values; or NULL */
   /* GroupNorm slab of row m (for stats_out and for the GN_GELU prologue):
    *   slab(m) = (m / stat_div) * stat_mul + (m % stat_mod)
@@ -100,6 +103,11 @@ int bd_istft_frames(const float* spec, const float* norm, const float* window, c
 /* K2b (htdemucs.py:449,653-659): out[B,S,2,Lout] = OLA(frames) + xt*stdt + meant; xt [B,Lseg,2S] or NULL. */
 int bd_ola_combine(const float* frames, const float* xt, const float* norm, float* out, int B, int S, int T, int Lseg,
                    int Lout, void* stream);
+
+/* K2 fused (same reference lines as K2a + K2b): spec [B,T,S,2048,4] source-major -> out [B,S,2,Lout], with the
+ * overlap-add done in shared memory (no frames buffer) and xt [B,Lseg,2S]*stdt+meant added (xt may be NULL). */
+int bd_istft_ola(const float* spec, const float* norm, const float* window, const float* twiddle, const float* xt,
+                 float* out, int B, int S, int T, int Lseg, int Lout, void* stream);
 
 /* K3/K4/K7: implicit-GEMM convolution / linear layer, see bd_gemm_desc. */
 int bd_conv_gemm(const bd_gemm_desc* desc, void* stream);

@@ -71,6 +71,23 @@ def bd_istft_frames(spec, norm, window, twiddle, frames, B, S, T, stream):
     f32(frames, B * S * 2 * T * 4096)[:] = fr.astype(np.float32).reshape(-1)
 
 
+def bd_istft_ola(spec, norm, window, twiddle, xt, out, B, S, T, Lseg, Lout, stream):
+    x = f32(spec, B * T * S * 2048 * 4).reshape(B, T, S, 2048, 2, 2)
+    nm = f32(norm, 8 * B).reshape(B, 8)
+    x = x * nm[:, 1].reshape(B, 1, 1, 1, 1, 1) + nm[:, 0].reshape(B, 1, 1, 1, 1, 1)
+    z = (x[..., 0] + 1j * x[..., 1]).transpose(0, 2, 4, 1, 3)             # [B,S,2,T,F]
+    z = np.concatenate([z, np.zeros_like(z[..., :1])], axis=-1)
+    fr = (np.fft.irfft(z, n=4096, axis=-1) * 64.0 * f32(window, 4096) / 1.5).astype(np.float32)
+    acc = np.zeros((B, S, 2, 1024 * (T - 1) + 4096), np.float32)
+    for t in range(T):
+        acc[..., t * 1024: t * 1024 + 4096] += fr[:, :, :, t]
+    res = acc[..., 1536: 1536 + Lout].copy()
+    if xt:
+        xv = f32(xt, B * Lseg * 2 * S).reshape(B, Lseg, S, 2)[:, :Lout].transpose(0, 2, 3, 1)
+        res += xv * nm[:, 5].reshape(B, 1, 1, 1) + nm[:, 4].reshape(B, 1, 1, 1)
+    f32(out, B * 2 * S * Lout)[:] = res.reshape(-1)
+
+
 def bd_ola_combine(frames, xt, norm, out, B, S, T, Lseg, Lout, stream):
     fr = f32(frames, B * S * 2 * T * 4096).reshape(B, 2 * S, T, 4096)
     acc = np.zeros((B, 2 * S, 1024 * (T - 1) + 4096), np.float32)
@@ -132,10 +149,12 @@ def bd_conv_gemm(dref, stream):
         r, co = n // cout, n % cout
         o0 = 4 * i0[:, None] + r[None, :] - (2 if d.convt == 1 else 0)
         ok = (o0 >= 0) & (o0 < d.O0)
-        oidx = (b * d.os_b + i1 * d.os_1)[:, None] + o0 * d.os_0 + co[None, :]
+        colofs = co if d.oc_split == 0 else (co // d.oc_split) * d.oc_stride + co % d.oc_split
+        oidx = (b * d.os_b + i1 * d.os_1)[:, None] + o0 * d.os_0 + colofs[None, :]
     else:
         ok = np.ones((M, nout), bool)
-        oidx = (b * d.os_b + i1 * d.os_1 + i0 * d.os_0)[:, None] + n[None, :]
+        colofs = n if d.oc_split == 0 else (n // d.oc_split) * d.oc_stride + n % d.oc_split
+        oidx = (b * d.os_b + i1 * d.os_1 + i0 * d.os_0)[:, None] + colofs[None, :]
     if d.rowbias:
         rb = f32(d.rowbias, d.rowbias_period * nout).reshape(d.rowbias_period, nout)
         v = v + rb[m % d.rowbias_period]

@@ -69,6 +69,18 @@ def test_stft_istft_kernels(L):
     torch.cuda.synchronize()
     want = istft_cac(z.double(), L)
     assert rel_l2(out.cpu(), want) < 1e-5
+    # fused variant: source-major spectrogram, overlap-add in shared memory, cropped output, + time branch
+    zs = z.permute(0, 4, 1, 3, 2).reshape(B, T, S, 2048, 4).contiguous().to(DEV)    # [B,T,S,F,(2c+reim)]
+    xt = torch.randn(B, L, 2 * S, generator=g).to(DEV)
+    norm[:, 4], norm[:, 5] = 0.25, 1.5
+    Lout = L - 37
+    out2 = torch.full((B, S, 2, Lout), float("nan"), device=DEV)
+    _lib.call("bd_istft_ola", zs.data_ptr(), norm.data_ptr(), eng.window.data_ptr(), eng.twiddle.data_ptr(),
+              xt.data_ptr(), out2.data_ptr(), B, S, T, L, Lout, 0)
+    torch.cuda.synchronize()
+    want2 = want[..., :Lout] + (xt.cpu().double()[:, :Lout] * 1.5 + 0.25).view(B, Lout, S, 2).permute(0, 2, 3, 1)
+    assert not torch.isnan(out2).any()
+    assert rel_l2(out2.cpu(), want2) < 1e-5
 
 
 def test_spectral_kernels_match_reference_golden():
