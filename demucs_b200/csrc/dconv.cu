@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
   float* sG = sB + N;                     // [N]   (FINAL)
   float* sBe = sG + N;                    // [N]   (FINAL)
   float* sS = sBe + N;                    // [C]   (FINAL)
+  float* sT = sS + C + (threadIdx.x >> 5) * (32 * 33);   // [32 rows][33] per warp (FINAL)
   for (int i = threadIdx.x; i < hid * N; i += DC_THREADS) sW[i] = __ldg(w2t + i);
   for (int i = threadIdx.x; i < N; i += DC_THREADS) {
     sB[i] = __ldg(b2 + i);
@@ -42,44 +43,43 @@ __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
   __syncthreads();
 
   // work item = (row, channel chunk): deep layers have few rows but wide C, so a row is split into `chunks`
-  // column ranges to keep enough threads in flight (each recomputes the row's short g vector)
+  // column ranges to keep enough threads in flight (each recomputes the row's short g vector).  Chunk-major
+  // order with the row count padded to a multiple of 32: the lanes of a warp work on 32 consecutive rows of
+  // the SAME column range, so the shared-memory weight reads are warp-uniform broadcasts.
   const int ncols = N / chunks;           // interleaved columns per chunk (multiple of 4)
-  const long long items = M * chunks;
-  // running statistics of the time branch (one GroupNorm item per batch item: consecutive rows share a slab)
-  long long run_slab = -1;
+  const long long Mp = (M + 31) & ~31LL;
+  const long long items = Mp * chunks;
+  long long run_slab = -1;                // running statistics (time branch: consecutive rows share a slab)
   float run_s = 0.f, run_q = 0.f;
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * DC_THREADS;
-  const long long base0 = (long long)blockIdx.x * DC_THREADS + threadIdx.x;
   for (long long it0 = (long long)blockIdx.x * DC_THREADS; it0 < items; it0 += stride) {
     const long long it = it0 + threadIdx.x;
-    (void)base0;
-    const bool live = it < items;
-    // chunk-major order: the lanes of a warp work on consecutive rows of the SAME column range, so the
-    // shared-memory weight reads stay warp-uniform broadcasts
-    const int chunk = live ? (int)(it / M) : 0;
-    const long long m = live ? it - (long long)chunk * M : 0;
+    const int chunk = (int)(it / Mp);                            // warp-uniform
+    const long long m = it - (long long)chunk * Mp;
+    const bool live = it < items && m < M;
+    const long long m_w = m - lane;                              // first row of this warp
     const int n_lo = chunk * ncols;
-    const long long slab = (m / rows_per_item) * slabs_per_item + (m % slabs_per_item);
-    float s = 0.f, q = 0.f;
+    const long long slab = live ? (m / rows_per_item) * slabs_per_item + (m % slabs_per_item) : 0;
+    float g[HID_T > 0 ? HID_T : MAX_HID];
+    float mean2 = 0.f, rstd2 = 1.f;
     if (live) {
       const float mean1 = __ldg(mr1 + 2 * slab), rstd1 = __ldg(mr1 + 2 * slab + 1);
-      float g[HID_T > 0 ? HID_T : MAX_HID];
       const float* hr = h + m * ldh;
 #pragma unroll
       for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k)
         if (k < hid) g[k] = bd_gelu(fmaf((__ldg(hr + k) - mean1) * rstd1, __ldg(g1 + k), __ldg(be1 + k)));
-      float mean2 = 0.f, rstd2 = 1.f;
       if (FINAL) {
         mean2 = __ldg(mr2 + 2 * slab);
         rstd2 = __ldg(mr2 + 2 * slab + 1);
       }
-      float* xr = FINAL ? x + m * C : nullptr;
-      float2 xnext = make_float2(0.f, 0.f);
-      if (FINAL) xnext = *reinterpret_cast<const float2*>(xr + (n_lo >> 1));
-      for (int n = n_lo; n < n_lo + ncols; n += 4) {   // 4 interleaved columns = (value, gate) of 2 channels
-        const float2 xv0 = xnext;                      // x of this group was requested one group ago
-        if (FINAL && n + 4 < n_lo + ncols) xnext = *reinterpret_cast<const float2*>(xr + ((n + 4) >> 1));
+    } else {
+#pragma unroll
+      for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k) g[k] = 0.f;
+    }
+    float s = 0.f, q = 0.f;
+    if (it0 + (threadIdx.x & ~31) < items) {                     // warp-uniform: this warp has work
+      for (int n = n_lo; n < n_lo + ncols; n += 4) {             // 4 interleaved columns = (value, gate) x 2 channels
         float4 u = *reinterpret_cast<const float4*>(sB + n);
 #pragma unroll
         for (int k = 0; k < (HID_T > 0 ? HID_T : MAX_HID); ++k) {
@@ -94,10 +94,30 @@ __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
           const float a0 = fmaf((u.x - mean2) * rstd2, ga.x, be.x), t0 = fmaf((u.y - mean2) * rstd2, ga.y, be.y);
           const float a1 = fmaf((u.z - mean2) * rstd2, ga.z, be.z), t1 = fmaf((u.w - mean2) * rstd2, ga.w, be.w);
           const float2 sc = *reinterpret_cast<const float2*>(sS + (n >> 1));
-          float2 xv = xv0;
-          xv.x = fmaf(sc.x, a0 * bd_sigmoid(t0), xv.x);
-          xv.y = fmaf(sc.y, a1 * bd_sigmoid(t1), xv.y);
-          *reinterpret_cast<float2*>(xr + (n >> 1)) = xv;
+          // x is updated 32 channels at a time: every lane parks the increments of ITS row in the warp's staging
+          // tile, then the warp walks its 32 rows with lane = channel -- each access to x is one 128-byte run
+          const int cc = (n - n_lo) >> 1;                        // channel inside the chunk
+          sT[lane * 33 + (cc & 31)] = sc.x * a0 * bd_sigmoid(t0);
+          sT[lane * 33 + (cc & 31) + 1] = sc.y * a1 * bd_sigmoid(t1);
+          if ((cc & 31) == 30 || n + 4 >= n_lo + ncols) {        // block of 32 channels complete (or chunk end)
+            const int c_lo = cc & ~31, width = cc + 2 - c_lo;
+            __syncwarp();
+            if (lane < width) {
+              float* xc = x + (n_lo >> 1) + c_lo + lane + m_w * C;
+              const int nrows = (int)(M - m_w < 32 ? M - m_w : 32);
+#pragma unroll 1
+              for (int r0 = 0; r0 < 32; r0 += 8) {               // 8 row loads in flight before the first store
+                float xv[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                  if (r0 + r < nrows) xv[r] = xc[(long long)(r0 + r) * C];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                  if (r0 + r < nrows) xc[(long long)(r0 + r) * C] = xv[r] + sT[(r0 + r) * 33 + lane];
+              }
+            }
+            __syncwarp();
+          }
         } else {
           s += (u.x + u.y) + (u.z + u.w);
           q = fmaf(u.x, u.x, fmaf(u.y, u.y, fmaf(u.z, u.z, fmaf(u.w, u.w, q))));
@@ -110,8 +130,8 @@ __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
       const long long slab0 = __shfl_sync(0xffffffffu, slab, 0);
       const bool uniform = __all_sync(0xffffffffu, !live || slab == slab0);
       if (uniform) {
-        const float ws = bd_warp_sum(s), wq = bd_warp_sum(q);
-        if (lane == 0) {
+        const float ws = bd_warp_sum(live ? s : 0.f), wq = bd_warp_sum(live ? q : 0.f);
+        if (lane == 0 && live) {
           if (slab0 != run_slab) {
             if (run_slab >= 0) {
               atomicAdd(&sums2[2 * run_slab], (double)run_s);
@@ -139,11 +159,11 @@ template <bool FINAL>
 int launch_expand(const float* h, int ldh, int hid, const float* mr1, const float* g1, const float* be1, const float* w2t,
                   const float* b2, double* sums2, const float* mr2, const float* g2, const float* be2, const float* scale,
                   float* x, long long M, int C, long long rpi, int spi, cudaStream_t st) {
-  const int smem = (hid * 2 * C + 2 * C * 3 + C) * (int)sizeof(float);
+  const int smem = (hid * 2 * C + 2 * C * 3 + C + (FINAL ? (DC_THREADS / 32) * 32 * 33 : 0)) * (int)sizeof(float);
   // split rows into channel chunks until ~256k work items exist (chunk = multiple of 2 channels)
   int chunks = 1;
   while (M * chunks < 262144 && chunks < 16 && (C % (4 * chunks)) == 0 && C / (2 * chunks) >= 8) chunks *= 2;
-  int grid = (int)((M * chunks + DC_THREADS - 1) / DC_THREADS);
+  int grid = (int)((((M + 31) & ~31LL) * chunks + DC_THREADS - 1) / DC_THREADS);
   const int cap = 148 * (smem > 96 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 8) * 2;   // grid-stride: weights staged once per CTA
   if (grid > cap) grid = cap;
 #define BD_DC_CASE(H)                                                                                             \

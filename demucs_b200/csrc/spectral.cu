@@ -284,9 +284,12 @@ __global__ void __launch_bounds__(NTHR) istft_ola_kernel(const float* __restrict
         const int n = j + r * NTHR;
         const float w = __ldg(win + n) * (1.0f / 64.0f / 1.5f);
         const int p = sidx(n);
-        const int ri = (t * 1024 + n) & (NFFT - 1);   // each thread owns its ring slots: no races
-        ring0[ri] += sre[p] * w;
-        ring1[ri] += sim[p] * w;
+        const int pos = t * 1024 + n;                 // position on the overlap-add grid
+        const int ri = pos & (NFFT - 1);              // each thread owns its ring slots: no races
+        if (pos >= h0 * 1024) {                       // halo frames only feed the hop blocks this CTA owns
+          ring0[ri] += sre[p] * w;
+          ring1[ri] += sim[p] * w;
+        }
       }
     }
     __syncthreads();
