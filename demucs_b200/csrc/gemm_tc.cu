@@ -68,6 +68,7 @@ struct TileGeom {
   int log2R0;
   int blocks0, blocks1;  // tiles along i0 / i1 per item
   int cpb;               // channel blocks per tap = Cin / TBK
+  int stride4;           // 1: k=8/s=4 convolution -- the position axis is viewed as (q, r) = (pos / 4, pos % 4)
 };
 constexpr uint32_t kSpinLimit = 1u << 26;          // turn a lost barrier into a trap, never a hang
 
@@ -119,6 +120,14 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
@@ -255,7 +264,12 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
         mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], kTileBytesA + kTileBytesB);
         // A: the tap-shifted window of the activation tensor; out-of-range rows/positions read as zero
-        tma_load_4d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, i0s + d.d0[tap], i1s + d.d1[tap], b);
+        if (g.stride4) {   // output position i0 reads input 4*i0 + d0 = 4*(i0 + floor(d0/4)) + (d0 mod 4)
+          const int d0 = d.d0[tap];
+          tma_load_5d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, d0 & 3, i0s + (d0 >> 2), i1s + d.d1[tap], b);
+        } else {
+          tma_load_4d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, i0s + d.d0[tap], i1s + d.d1[tap], b);
+        }
         tma_load_2d(&map_b, &full_bar[s], sB + s * kStageBytesB, tap * d.Cin + cb * TBK, n0);
         if (++cb == g.cpb) {
           cb = 0;
@@ -473,7 +487,7 @@ bool encode(CUtensorMap* map, const float* base, int rank, const cuuint64_t* gdi
             const cuuint32_t* box, int tbk) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, gdim, gstride_bytes, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, tbk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -491,13 +505,20 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
   alignas(64) CUtensorMap map_a, map_b;
   // activations: (c, j0, j1, item); size-1 axes get a harmless contiguous stride
   const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
-  cuuint64_t adim[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.J0, (cuuint64_t)d.J1, (cuuint64_t)items};
-  cuuint64_t astr[3] = {(cuuint64_t)s0 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)sb * 4};
-  cuuint32_t abox[4] = {(cuuint32_t)TBK, (cuuint32_t)g.R0, (cuuint32_t)g.R1, 1};
+  cuuint64_t adim[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.J0, (cuuint64_t)d.J1, (cuuint64_t)items, 1};
+  cuuint64_t astr[4] = {(cuuint64_t)s0 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)sb * 4, 0};
+  cuuint32_t abox[5] = {(cuuint32_t)TBK, (cuuint32_t)g.R0, (cuuint32_t)g.R1, 1, 1};
+  int arank = 4;
+  if (g.stride4) {   // (c, r = pos % 4, q = pos / 4, j1, item)
+    arank = 5;
+    adim[1] = 4; adim[2] = (cuuint64_t)d.J0 / 4; adim[3] = (cuuint64_t)d.J1; adim[4] = (cuuint64_t)items;
+    astr[0] = (cuuint64_t)s0 * 4; astr[1] = (cuuint64_t)s0 * 16; astr[2] = (cuuint64_t)s1 * 4; astr[3] = (cuuint64_t)sb * 4;
+    abox[1] = 1; abox[2] = (cuuint32_t)g.R0; abox[3] = (cuuint32_t)g.R1; abox[4] = 1;
+  }
   cuuint64_t bdim[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
   cuuint64_t bstr[1] = {(cuuint64_t)d.K * 4};
   cuuint32_t bbox[2] = {(cuuint32_t)TBK, (cuuint32_t)TBN};   // weight rows past N are zero-filled
-  if (!encode(&map_a, d.x, 4, adim, astr, abox, TBK) || !encode(&map_b, d.w, 2, bdim, bstr, bbox, TBK)) {
+  if (!encode(&map_a, d.x, arank, adim, astr, abox, TBK) || !encode(&map_b, d.w, 2, bdim, bstr, bbox, TBK)) {
     bd_set_error("bd_conv_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d Cin=%d J0=%d J1=%d)", d.M, d.N, d.K,
                  d.Cin, d.J0, d.J1);
     return BD_ERR_CUDA;
@@ -524,7 +545,8 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
 
 // eligibility: unit-stride implicit GEMM, channels-last, big enough to fill tensor-core tiles
 bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d) {
-  if (d.a_mode != BD_A_NONE || d.xs_c != 1 || d.m0 != 1 || d.m1 != 1) return false;
+  if (d.a_mode != BD_A_NONE || d.xs_c != 1 || d.m1 != 1) return false;
+  if (!(d.m0 == 1 || (d.m0 == 4 && d.J0 % 4 == 0))) return false;
   if (d.Cin % 16 != 0 || d.N < 16 || d.K < 16 || d.M < 128 || d.taps > BD_MAX_TAPS) return false;
   if (d.xs_0 % 4 != 0 || (d.J1 > 1 && d.xs_1 % 4 != 0) || d.xs_b % 4 != 0) return false;
   if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15)) return false;
@@ -545,6 +567,7 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   while ((1 << g.log2R0) < g.R0) ++g.log2R0;
   g.blocks0 = (d.I0 + g.R0 - 1) / g.R0;
   g.blocks1 = (d.I1 + g.R1 - 1) / g.R1;
+  g.stride4 = d.m0 == 4;
   const int items = d.M / (d.I0 * d.I1);
   int rc;
   const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;

@@ -380,6 +380,9 @@ class Engine:
         T = cfg.frames(L)
         chans = cfg.enc_channels
 
+        def tp(n):   # time-branch item pitch: rows padded to a multiple of 4
+            return (n + 3) // 4 * 4
+
         def tap(name, t, fmt):
             if taps is None:
                 return
@@ -404,23 +407,28 @@ class Engine:
         xf, Fin, Cin = spec, 2048, 2 * A
         xt, Cin_t = mix, A
         for i, Cc in enumerate(chans):
-            # time branch: Conv1d(k=8,s=4,p=2) on the right-padded signal -> GELU (hdemucs.py:131-144)
+            # time branch: Conv1d(k=8,s=4,p=2) on the right-padded signal -> GELU (hdemucs.py:131-144).
+            # Skip tensors are stored with the item length padded to a multiple of 4 (zero rows): that is the
+            # reference's own right-padding (hdemucs.py:132-135) and lets the next layer's stride-4 window be
+            # a (pos/4, pos%4) TMA box.
             Tin, Tout = tl[i], tl[i + 1]
             y = self._buf(key, "y_t", B * Tout * Cc)
             first = i == 0
+            Tin_p = Tin if first else tp(Tin)
             self._gemm(M=B * Tout, N=Cc, Cin=Cin_t, x=xt, w=W[f"tencoder.{i}.conv.w"], bias=W[f"tencoder.{i}.conv.b"],
-                       out=y, taps=tuple((0, k - 2) for k in range(8)), I1=1, I0=Tout, m0=4, J1=1, J0=Tin,
-                       xs=(A * L, 0, 1, L) if first else (Tin * Cin_t, 0, Cin_t, 1), os_=(Tout * Cc, 0, Cc),
+                       out=y, taps=tuple((0, k - 2) for k in range(8)), I1=1, I0=Tout, m0=4, J1=1, J0=Tin_p,
+                       xs=(A * L, 0, 1, L) if first else (Tin_p * Cin_t, 0, Cin_t, 1), os_=(Tout * Cc, 0, Cc),
                        a_mode=_lib.A_ITEM_AFFINE if first else _lib.A_NONE,
                        a_stats=norm[4:] if first else None, a_stats_stride=8, act=_lib.ACT_GELU)
             if cfg.dconv_mode & 1:
                 self._dconv(key, f"tencoder.{i}", y, B, Tout, 1, Cc, "_t")
-            z = self._buf(key, f"saved_t{i}", B * Tout * Cc)
+            z = self._buf(key, f"saved_t{i}", B * tp(Tout) * Cc, zero=True)
             self._gemm(M=B * Tout, N=2 * Cc, Cin=Cc, x=y, w=W[f"tencoder.{i}.rewrite.w"],
-                       bias=W[f"tencoder.{i}.rewrite.b"], out=z, act=_lib.ACT_GLU)
+                       bias=W[f"tencoder.{i}.rewrite.b"], out=z, act=_lib.ACT_GLU, I1=1, I0=Tout, J1=1, J0=Tout,
+                       xs=(Tout * Cc, 0, Cc, 1), os_=(tp(Tout) * Cc, 0, Cc))
             saved_t.append(z)
             xt, Cin_t = z, Cc
-            tap(f"tenc{i}", z.view(B, Tout, Cc), "t")
+            tap(f"tenc{i}", z.view(B, tp(Tout), Cc)[:, :Tout], "t")
 
             # frequency branch: Conv2d(k=(8,1),s=(4,1),p=(2,0)) -> GELU
             Fo = Fin // 4
@@ -445,7 +453,7 @@ class Engine:
         Mf, Mt = B * T * Fb, B * T2
         # ping-pong buffers of the decoders, sized for their largest activation
         dec_f_numel = B * T * max(2048 * 4 * S, 512 * chans[0])
-        dec_t_numel = B * max(L * 2 * S, tl[1] * chans[0])
+        dec_t_numel = B * max(tp(L) * 2 * S, tp(tl[1]) * chans[0])
 
         # ---- cross-domain transformer ------------------------------------------------------------
         if cfg.t_layers > 0:
@@ -455,12 +463,12 @@ class Engine:
                 xt_ = self._buf(key, "tr_xt", Mt * D)
                 self._gemm(M=Mf, N=D, Cin=Cb, x=xf, w=W["channel_upsampler.w"], bias=W["channel_upsampler.b"], out=x)
                 self._gemm(M=Mt, N=D, Cin=Cb, x=xt, w=W["channel_upsampler_t.w"], bias=W["channel_upsampler_t.b"],
-                           out=xt_)
+                           out=xt_, I1=1, I0=T2, J1=1, J0=T2, xs=(tp(T2) * Cb, 0, Cb, 1), os_=(T2 * D, 0, D))
             else:
                 x = self._buf(key, "tr_x", Mf * D)
                 xt_ = self._buf(key, "tr_xt", Mt * D)
                 x.copy_(xf)
-                xt_.copy_(xt)
+                xt_.view(B, T2, D).copy_(xt.view(B, tp(T2), Cb)[:, :T2])
             ct = "crosstransformer"
             pos2d = self._pos_table(("2d", Fb, T))
             pos1d = self._pos_table(("1d", T2))
@@ -482,23 +490,24 @@ class Engine:
                 tap(f"xt.layer{i}", xt_.view(B, T2, D), "t")
             # channel_downsampler (+ the decoder's skip add, hdemucs.py:310, fused as `addend`)
             xd = self._buf(key, "dec_a", dec_f_numel)[: Mf * Cb]
-            xtd = self._buf(key, "dec_ta", dec_t_numel)[: Mt * Cb]
+            xtd = self._buf(key, "dec_ta", dec_t_numel)[: B * tp(T2) * Cb]
             if cfg.bottom_channels:
                 self._gemm(M=Mf, N=Cb, Cin=D, x=x, w=W["channel_downsampler.w"], bias=W["channel_downsampler.b"],
                            out=xd, addend=saved[-1])
                 self._gemm(M=Mt, N=Cb, Cin=D, x=xt_, w=W["channel_downsampler_t.w"],
-                           bias=W["channel_downsampler_t.b"], out=xtd, addend=saved_t[-1])
+                           bias=W["channel_downsampler_t.b"], out=xtd, addend=saved_t[-1], I1=1, I0=T2, J1=1, J0=T2,
+                           xs=(T2 * D, 0, D, 1), os_=(tp(T2) * Cb, 0, Cb))
             else:
                 torch.add(x, saved[-1], out=xd)
-                torch.add(xt_, saved_t[-1], out=xtd)
+                xtd.view(B, tp(T2), Cb)[:, :T2].copy_(xt_.view(B, T2, Cb) + saved_t[-1].view(B, tp(T2), Cb)[:, :T2])
             if taps is not None:
                 tap("bottleneck", (xd - saved[-1]).view(B, T, Fb, Cb), "f")
-                tap("bottleneck_t", (xtd - saved_t[-1]).view(B, T2, Cb), "t")
+                tap("bottleneck_t", (xtd - saved_t[-1]).view(B, tp(T2), Cb)[:, :T2], "t")
         else:
             xd = self._buf(key, "dec_a", dec_f_numel)[: Mf * Cb]
-            xtd = self._buf(key, "dec_ta", dec_t_numel)[: Mt * Cb]
+            xtd = self._buf(key, "dec_ta", dec_t_numel)[: B * tp(T2) * Cb]
             torch.add(xf, saved[-1], out=xd)
-            torch.add(xt, saved_t[-1], out=xtd)
+            torch.mul(saved_t[-1], 2.0, out=xtd)    # no transformer: x + skip with skip == x
 
         # ---- decoders ------------------------------------------------------------------------------
         Fcur = Fb
@@ -543,31 +552,31 @@ class Engine:
             y = self._buf(key, "y_t", B * Tin * Cc)
             self._gemm(M=B * Tin, N=2 * Cc, Cin=Cc, x=xtd, w=W[f"tdecoder.{j}.rewrite.w"],
                        bias=W[f"tdecoder.{j}.rewrite.b"], out=y, taps=((0, -1), (0, 0), (0, 1)), I1=1, I0=Tin,
-                       J1=1, J0=Tin, xs=(Tin * Cc, 0, Cc, 1), os_=(Tin * Cc, 0, Cc), act=_lib.ACT_GLU)
+                       J1=1, J0=Tin, xs=(tp(Tin) * Cc, 0, Cc, 1), os_=(Tin * Cc, 0, Cc), act=_lib.ACT_GLU)
             if cfg.dconv_mode & 2:
                 self._dconv(key, f"tdecoder.{j}", y, B, Tin, 1, Cc, "_t")
-            nxt = self._buf(key, "dec_tb" if (j % 2 == 0) else "dec_ta", dec_t_numel)[: B * Tout * Cout_t]
+            nxt = self._buf(key, "dec_tb" if (j % 2 == 0) else "dec_ta", dec_t_numel)[: B * tp(Tout) * Cout_t]
             three = self.mode != "fp32" and 4 * Cout_t >= 64
             self._gemm(M=B * (Tin + (0 if three else 1)), N=4 * Cout_t, Cin=Cc, x=y,
                        w=W[f"tdecoder.{j}.conv_tr.w3" if three else f"tdecoder.{j}.conv_tr.w"],
                        bias=W[f"tdecoder.{j}.conv_tr.b"], out=nxt,
                        taps=((0, -1), (0, 0), (0, 1)) if three else ((0, 0), (0, -1)), I1=1,
                        I0=Tin + (0 if three else 1), J1=1, J0=Tin, xs=(Tin * Cc, 0, Cc, 1),
-                       os_=(Tout * Cout_t, 0, Cout_t), convt=2 if three else 1, O0=Tout,
+                       os_=(tp(Tout) * Cout_t, 0, Cout_t), convt=2 if three else 1, O0=Tout,
                        act=_lib.ACT_NONE if last else _lib.ACT_GELU, addend=skip_t)
             if taps is not None:
-                tap(f"tdec{j}", (nxt - skip_t if skip_t is not None else nxt).view(B, Tout, Cout_t), "t")
+                tap(f"tdec{j}", (nxt - skip_t if skip_t is not None else nxt).view(B, tp(Tout), Cout_t)[:, :Tout], "t")
             xtd = nxt
 
         # ---- K2: de-normalise, iSTFT, overlap-add in shared memory, crop, add the time branch ------------
         out = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
         self._k("bd_istft_ola", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), ptr(xtd), ptr(out),
-                B, S, T, L, L0, st, nbytes=4.0 * B * S * (T * 2048 * 4 + 2 * L + 2 * L0),
+                B, S, T, tp(L), L0, st, nbytes=4.0 * B * S * (T * 2048 * 4 + 2 * L + 2 * L0),
                 flops=2.5 * 4096 * 12 * 2 * S * B * T)
         if taps is not None:
             only = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
             self._k("bd_istft_ola", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), None, ptr(only),
-                    B, S, T, L, L0, st)
+                    B, S, T, tp(L), L0, st)
             taps["istft"] = only
             taps["time_out"] = out - only
         return out
