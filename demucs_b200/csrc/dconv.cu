@@ -11,10 +11,9 @@
 
 namespace {
 
-constexpr int DC_THREADS = 128;
 constexpr int MAX_HID = 48;
 
-template <int HID_T, bool FINAL>
+template <int HID_T, bool FINAL, int DC_THREADS>
 __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
     const float* __restrict__ h, int ldh, int hid_rt, const float* __restrict__ mr1, const float* __restrict__ g1,
     const float* __restrict__ be1, const float* __restrict__ w2t /*[hid][2C] interleaved*/, const float* __restrict__ b2,
@@ -155,39 +154,42 @@ __global__ void __launch_bounds__(DC_THREADS) dconv_expand_kernel(
   }
 }
 
-template <bool FINAL>
-int launch_expand(const float* h, int ldh, int hid, const float* mr1, const float* g1, const float* be1, const float* w2t,
-                  const float* b2, double* sums2, const float* mr2, const float* g2, const float* be2, const float* scale,
-                  float* x, long long M, int C, long long rpi, int spi, cudaStream_t st) {
-  const int smem = (hid * 2 * C + 2 * C * 3 + C + (FINAL ? (DC_THREADS / 32) * 32 * 33 : 0)) * (int)sizeof(float);
+template <int HID_T, bool FINAL, int THREADS>
+int launch_one(const float* h, int ldh, int hid, const float* mr1, const float* g1, const float* be1, const float* w2t,
+               const float* b2, double* sums2, const float* mr2, const float* g2, const float* be2, const float* scale,
+               float* x, long long M, int C, long long rpi, int spi, int ctas_per_sm, cudaStream_t st) {
+  const int smem = (hid * 2 * C + 2 * C * 3 + C + (FINAL ? (THREADS / 32) * 32 * 33 : 0)) * (int)sizeof(float);
   // split rows into channel chunks until ~256k work items exist (chunk = multiple of 2 channels)
   int chunks = 1;
   while (M * chunks < 262144 && chunks < 16 && (C % (4 * chunks)) == 0 && C / (2 * chunks) >= 8) chunks *= 2;
-  int grid = (int)((((M + 31) & ~31LL) * chunks + DC_THREADS - 1) / DC_THREADS);
-  const int cap = 148 * (smem > 96 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 8) * 2;   // grid-stride: weights staged once per CTA
+  long long grid = ((((M + 31) & ~31LL) * chunks + THREADS - 1) / THREADS);
+  const long long cap = 148LL * ctas_per_sm * 2;   // grid-stride: weights are staged once per CTA
   if (grid > cap) grid = cap;
-#define BD_DC_CASE(H)                                                                                             \
-  if (hid == H) {                                                                                                 \
-    cudaError_t e = cudaFuncSetAttribute(dconv_expand_kernel<H, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         smem);                                                                   \
-    if (e != cudaSuccess) {                                                                                       \
-      bd_set_error("bd_dconv_expand: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                           \
-      return BD_ERR_CUDA;                                                                                         \
-    }                                                                                                             \
-    dconv_expand_kernel<H, FINAL><<<grid, DC_THREADS, smem, st>>>(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2,  \
-                                                                  be2, scale, x, M, C, rpi, spi, chunks);         \
-    return bd_check_launch("dconv_expand_kernel");                                                                \
-  }
-  BD_DC_CASE(6) BD_DC_CASE(12) BD_DC_CASE(24) BD_DC_CASE(48)
-#undef BD_DC_CASE
-  cudaError_t e = cudaFuncSetAttribute(dconv_expand_kernel<0, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(dconv_expand_kernel<HID_T, FINAL, THREADS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     bd_set_error("bd_dconv_expand: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return BD_ERR_CUDA;
   }
-  dconv_expand_kernel<0, FINAL><<<grid, DC_THREADS, smem, st>>>(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2, be2,
-                                                                scale, x, M, C, rpi, spi, chunks);
+  dconv_expand_kernel<HID_T, FINAL, THREADS><<<(unsigned)grid, THREADS, smem, st>>>(
+      h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2, be2, scale, x, M, C, rpi, spi, chunks);
   return bd_check_launch("dconv_expand_kernel");
+}
+
+template <bool FINAL>
+int launch_expand(const float* h, int ldh, int hid, const float* mr1, const float* g1, const float* be1, const float* w2t,
+                  const float* b2, double* sums2, const float* mr2, const float* g2, const float* be2, const float* scale,
+                  float* x, long long M, int C, long long rpi, int spi, cudaStream_t st) {
+#define BD_DC_ARGS h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, mr2, g2, be2, scale, x, M, C, rpi, spi
+  // narrow layers: many small CTAs; wide layers (W2 of 36..147 KB in shared memory): one big CTA per SM
+  if (hid == 6) return launch_one<6, FINAL, 128>(BD_DC_ARGS, 8, st);
+  if (hid == 12) return launch_one<12, FINAL, 128>(BD_DC_ARGS, 8, st);
+  if (hid == 24) return launch_one<24, FINAL, 256>(BD_DC_ARGS, 2, st);
+  if (hid == 48) return launch_one<48, FINAL, 512>(BD_DC_ARGS, 1, st);
+  const int wbytes = hid * 2 * C * 4;
+  if (wbytes > 64 * 1024) return launch_one<0, FINAL, 512>(BD_DC_ARGS, 1, st);
+  return launch_one<0, FINAL, 128>(BD_DC_ARGS, wbytes > 24 * 1024 ? 2 : 8, st);
+#undef BD_DC_ARGS
 }
 
 }  // namespace
