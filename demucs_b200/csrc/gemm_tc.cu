@@ -31,6 +31,9 @@
 
 namespace {
 
+#ifndef BD_TC_PIPE_BYTES
+#define BD_TC_PIPE_BYTES 98304
+#endif
 constexpr int TBM = 128;                           // tile rows (UMMA M)
 constexpr int kThreads = 192;
 
@@ -42,7 +45,7 @@ template <int TBK, int TBN, bool X3>
 struct Cfg {
   static constexpr int kTileBytesA = TBM * TBK * 4, kTileBytesB = TBN * TBK * 4;
   static constexpr int kStageBytesA = kTileBytesA * (X3 ? 2 : 1), kStageBytesB = kTileBytesB * (X3 ? 2 : 1);
-  static constexpr int kStagesRaw = (X3 ? 196608 : 98304) / (kStageBytesA + kStageBytesB);   // 96 KB: 2 CTAs / SM
+  static constexpr int kStagesRaw = (X3 ? 196608 : BD_TC_PIPE_BYTES) / (kStageBytesA + kStageBytesB);   // 96 KB: 2 CTAs / SM
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kStagingBytes = 4 * 32 * (TBN + 4) * 4;
   static constexpr int kTailBytes = 512 /*barriers*/ + 128 * 32 /*RowInfo*/;
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     const bool vec = bd_epi_vec_ok(d);
     constexpr int LDT = TBN + 4;            // staging row pitch (floats): conflict-free float4 rows
     float* stage = reinterpret_cast<float*>(smem) + (size_t)quarter * 32 * LDT;
-    RowInfo* rinfo = reinterpret_cast<RowInfo*>(tmem_slot + 4) + quarter * 32;
+    RowInfo* rinfo = reinterpret_cast<RowInfo*>(((uintptr_t)(tmem_slot + 4) + 31) & ~(uintptr_t)31) + quarter * 32;
     if (vec) {
       rinfo[lane].obase = er.obase;
       rinfo[lane].i0 = row_ok ? er.i0 : -1;
@@ -382,7 +385,18 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
           const int rloc = (it + u) * RPI + rsub;
-          const RowInfo ri = rinfo[rloc];
+          RowInfo ri;                        // explicit ld.shared (the compiler had demoted these to generic loads)
+          {
+            const uint32_t a = smem_u32(&rinfo[rloc]);
+            uint32_t w0, w1, w2, w3, w4, w5;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w4), "=r"(w5) : "r"(a + 16));
+            ri.obase = (long long)(((unsigned long long)w1 << 32) | w0);
+            ri.i0 = (int)w2;
+            ri.rb_row = (int)w3;
+            ri.e_mean = __uint_as_float(w4);
+            ri.e_rstd = __uint_as_float(w5);
+          }
           row[u].obase = ri.obase; row[u].i0 = ri.i0; row[u].rb_row = ri.rb_row;
           row[u].e_mean = ri.e_mean; row[u].e_rstd = ri.e_rstd;
           ok[u] = (it + u) * RPI < 32 && ri.i0 >= 0 && col_ok;
