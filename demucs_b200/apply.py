@@ -233,7 +233,7 @@ def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor,
             return
     eng._k("bd_overlap_add", ptr(segs), ptr(weight), ptr(out), first, n_local, nseg, rows, valid, seg_len, stride,
            ps.length, out.shape[-1], ps.out_shift, n_begin, n_end, ptr(row_alpha), ps.alpha, int(accumulate),
-           eng._stream())
+           eng._stream(), nbytes=4.0 * rows * (n_local * min(seg_len, ps.length) + (n_end - n_begin) * (2 if accumulate else 1)))
 
 
 def apply_model(model: tp.Union[BagOfModels, Model],

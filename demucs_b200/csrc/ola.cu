@@ -12,37 +12,52 @@
 
 namespace {
 
+constexpr int OLA_VEC = 4;   // consecutive samples per thread (independent loads in flight)
+
 __global__ void overlap_add_kernel(const float* __restrict__ segs, const float* __restrict__ weight,
                                    float* __restrict__ out, int seg_first, int nseg_local, int nseg, int rows, int valid,
                                    int seg_len, int stride, long long length, long long out_ld, long long out_shift,
                                    long long n_begin, long long n_end, const float* __restrict__ row_alpha, float alpha,
                                    int accumulate) {
-  const long long n = n_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nb = n_begin + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * OLA_VEC;
   const int r = blockIdx.y;
-  if (n >= n_end) return;
-  int i_hi = (int)(n / stride);
+  if (nb >= n_end) return;
+  // all OLA_VEC samples of this thread see the same candidate segments except at segment edges, which the
+  // per-sample bounds below handle; a sharded caller holds segments [seg_first, seg_first + nseg_local)
+  int i_hi = (int)((nb + OLA_VEC - 1) / stride);
   if (i_hi > nseg - 1) i_hi = nseg - 1;
-  long long lo = n - seg_len + 1;
+  long long lo = nb - seg_len + 1;
   int i_lo = lo <= 0 ? 0 : (int)((lo + stride - 1) / stride);
-  // a sharded caller holds segments [seg_first, seg_first + nseg_local); it must own sample n entirely
   if (i_lo < seg_first) i_lo = seg_first;
   if (i_hi > seg_first + nseg_local - 1) i_hi = seg_first + nseg_local - 1;
-  float num = 0.f, den = 0.f;
+  float num[OLA_VEC], den[OLA_VEC];
+#pragma unroll
+  for (int v = 0; v < OLA_VEC; ++v) num[v] = den[v] = 0.f;
   for (int i = i_lo; i <= i_hi; ++i) {
     const long long off = (long long)i * stride;
-    const int k = (int)(n - off);
     long long rem = length - off;
     const int n_i = rem < seg_len ? (int)rem : seg_len;   // TensorChunk length clip (apply.py:91-94)
-    if (k >= n_i) continue;
     const int lead = (valid - n_i) / 2;                    // centre trim (utils.py:52-53)
-    const float w = __ldg(weight + k);
-    num = fmaf(w, __ldg(segs + ((size_t)(i - seg_first) * rows + r) * valid + lead + k), num);
-    den += w;
+    const float* sp = segs + ((size_t)(i - seg_first) * rows + r) * valid + lead;
+#pragma unroll
+    for (int v = 0; v < OLA_VEC; ++v) {
+      const long long k = nb + v - off;
+      if (k >= 0 && k < n_i && nb + v < n_end) {
+        const float w = __ldg(weight + k);
+        num[v] = fmaf(w, __ldg(sp + k), num[v]);
+        den[v] += w;
+      }
+    }
   }
-  float v = num / den;
-  v *= alpha * (row_alpha ? __ldg(row_alpha + r) : 1.f);
-  float* o = out + (size_t)r * out_ld + (n - out_shift);
-  *o = accumulate ? *o + v : v;
+  const float a = alpha * (row_alpha ? __ldg(row_alpha + r) : 1.f);
+  float* o = out + (size_t)r * out_ld + (nb - out_shift);
+#pragma unroll
+  for (int v = 0; v < OLA_VEC; ++v) {
+    if (nb + v < n_end) {
+      const float val = num[v] / den[v] * a;
+      o[v] = accumulate ? o[v] + val : val;
+    }
+  }
 }
 
 }  // namespace
@@ -60,7 +75,7 @@ extern "C" int bd_overlap_add(const float* segs, const float* weight, float* out
   if (n_begin < out_shift) n_begin = out_shift;
   if (n_end > length) n_end = length;
   if (n_end <= n_begin) return BD_OK;
-  overlap_add_kernel<<<dim3(bd_cdiv(n_end - n_begin, 256), rows), 256, 0, (cudaStream_t)stream>>>(
+  overlap_add_kernel<<<dim3(bd_cdiv(n_end - n_begin, 256 * OLA_VEC), rows), 256, 0, (cudaStream_t)stream>>>(
       segs, weight, out, seg_first, nseg_local, nseg, rows, valid, seg_len, stride, length, out_ld, out_shift, n_begin,
       n_end, row_alpha, alpha, accumulate);
   return bd_check_launch("overlap_add_kernel");

@@ -102,12 +102,12 @@ __global__ void __launch_bounds__(NTHR) stft_cac_kernel(const float* __restrict_
                                                         double* __restrict__ stats, int L, int T) {
   __shared__ float sre[SPAD];
   __shared__ float sim[SPAD];
-  __shared__ double red[64];
+  __shared__ float red[4][16];
   const int t = blockIdx.x, b = blockIdx.y, j = threadIdx.x;
   const float* x0 = mix + (size_t)b * 2 * L;
   const float* x1 = x0 + L;
   float2 v[8];
-  double ts = 0.0, tq = 0.0;
+  float ts = 0.f, tq = 0.f;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int n = j + r * NTHR;
@@ -117,14 +117,14 @@ __global__ void __launch_bounds__(NTHR) stft_cac_kernel(const float* __restrict_
     src = src >= L ? 2 * (L - 1) - src : src;
     const float a = __ldg(x0 + src), c = __ldg(x1 + src), w = __ldg(win + n);
     if (own) {
-      ts += (double)a + (double)c;
-      tq += (double)a * a + (double)c * c;
+      ts += a + c;
+      tq = fmaf(a, a, fmaf(c, c, tq));
     }
     v[r] = make_float2(a * w, c * w);
   }
   fft4096<-1>(v, sre, sim, tw);
   float4* out = reinterpret_cast<float4*>(spec) + ((size_t)b * T + t) * 2048;
-  double fs = 0.0, fq = 0.0;
+  float fs = 0.f, fq = 0.f;
   const float sc = 1.0f / 128.0f;  // 1/2 (channel split) * 1/sqrt(4096) (normalized=True)
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -133,18 +133,20 @@ __global__ void __launch_bounds__(NTHR) stft_cac_kernel(const float* __restrict_
     const float zr = sre[pf], zi = sim[pf], mr = sre[pm], mi = sim[pm];
     float4 o = make_float4((zr + mr) * sc, (zi - mi) * sc, (zi + mi) * sc, (mr - zr) * sc);
     out[f] = o;
-    fs += (double)o.x + (double)o.y + (double)o.z + (double)o.w;
-    fq += (double)o.x * o.x + (double)o.y * o.y + (double)o.z * o.z + (double)o.w * o.w;
+    fs += (o.x + o.y) + (o.z + o.w);
+    fq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, fq))));
   }
-  bd_block_sum2(fs, fq, red);
-  if (j == 0) {
-    atomicAdd(&stats[b * 4 + 0], fs);
-    atomicAdd(&stats[b * 4 + 1], fq);
+  // one frame's partial sums (<= 8192 values) in fp32, frames combined in fp64
+  fs = bd_warp_sum(fs); fq = bd_warp_sum(fq); ts = bd_warp_sum(ts); tq = bd_warp_sum(tq);
+  if ((j & 31) == 0) {
+    red[0][j >> 5] = fs; red[1][j >> 5] = fq; red[2][j >> 5] = ts; red[3][j >> 5] = tq;
   }
-  bd_block_sum2(ts, tq, red);
-  if (j == 0) {
-    atomicAdd(&stats[b * 4 + 2], ts);
-    atomicAdd(&stats[b * 4 + 3], tq);
+  __syncthreads();
+  if (j < 4) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) acc += (double)red[j][w];
+    atomicAdd(&stats[b * 4 + j], acc);
   }
 }
 
@@ -241,7 +243,7 @@ __global__ void ola_combine_kernel(const float* __restrict__ frames, const float
 // (spectrogram in, waveform out) is the only traffic, bar the 3 recomputed halo frames per chunk.
 constexpr int NH = 24;
 
-__global__ void __launch_bounds__(NTHR) istft_ola_kernel(const float* __restrict__ spec, const float* __restrict__ norm,
+__global__ void __launch_bounds__(NTHR, 2) istft_ola_kernel(const float* __restrict__ spec, const float* __restrict__ norm,
                                                          const float* __restrict__ win, const float2* __restrict__ tw,
                                                          const float* __restrict__ xt, float* __restrict__ out, int S,
                                                          int T, int Lseg, int Lout) {
