@@ -83,6 +83,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     import hashlib
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("BD_NVCC_DEFS", "").split()     # experiment knobs, e.g. -DBD_TC_PIPE_BYTES=196608
     digest = hashlib.sha256(" ".join(flags).encode())
     for dep in sorted(set(deps)):
         with open(dep, "rb") as f:

@@ -7,7 +7,7 @@
 #include "../../include/demucs_b200.h"
 
 struct EpiRow {
-  long long obase;   // b*os_b + i1*os_1
+  long long obase;   // b*os_b + i1*os_1 + (first output position of the row)*os_0
   int i0;
   int rb_row;        // m % rowbias_period
   float e_mean, e_rstd;
@@ -25,7 +25,8 @@ __device__ __forceinline__ EpiRow bd_epi_row(const bd_gemm_desc& d, long long m6
   r.i0 = (int)(m - t * (unsigned)d.I0);
   const unsigned b = t / (unsigned)d.I1;
   const int i1 = (int)(t - b * (unsigned)d.I1);
-  r.obase = (long long)b * d.os_b + (long long)i1 * d.os_1;
+  r.obase = (long long)b * d.os_b + (long long)i1 * d.os_1 +
+            (long long)(d.convt ? 4 * r.i0 - (d.convt == 1 ? 2 : 0) : r.i0) * d.os_0;
   r.rb_row = d.rowbias ? (int)(m % (unsigned)d.rowbias_period) : 0;
   r.e_mean = 0.f;
   r.e_rstd = 1.f;
@@ -59,53 +60,13 @@ __device__ __forceinline__ long long bd_col_ofs(const bd_gemm_desc& d, int no) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
-// Memory-side operands of one 4-column group: output offset plus the residual / skip / embedding
-// values, fetched BEFORE any arithmetic so that a caller can put several groups' loads in flight
-// (the in-place residual update makes loads and stores alias, which stops the compiler from doing it).
-struct EpiMem {
-  long long o;       // output offset of the first stored element, -1: nothing to store
-  int no;
-  float4 resid, addend, rowbias;
-};
-
-__device__ __forceinline__ EpiMem bd_epi_fetch4(const bd_gemm_desc& d, const EpiRow& r, int n) {
-  EpiMem e;
-  e.resid = e.addend = e.rowbias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (d.act == BD_ACT_GLU) {
-    e.no = n >> 1;
-    const int Nout = d.N >> 1;
-    e.o = r.obase + (long long)r.i0 * d.os_0 + bd_col_ofs(d, e.no);
-    if (d.rowbias) { const float2 t = ldg2(d.rowbias + (size_t)r.rb_row * Nout + e.no); e.rowbias.x = t.x; e.rowbias.y = t.y; }
-    if (d.resid) { const float2 t = ldg2(d.resid + e.o); e.resid.x = t.x; e.resid.y = t.y; }
-    if (d.addend) { const float2 t = ldg2(d.addend + e.o); e.addend.x = t.x; e.addend.y = t.y; }
-    return e;
-  }
-  int Nout = d.N;
-  e.no = n;
-  if (d.convt) {
-    const int Cout = d.N >> 2;
-    const int rr = n / Cout;
-    const int o0 = 4 * r.i0 + rr - (d.convt == 1 ? 2 : 0);
-    if (o0 < 0 || o0 >= d.O0) {
-      e.o = -1;
-      return e;
-    }
-    e.no = n - rr * Cout;
-    Nout = Cout;
-    e.o = r.obase + (long long)o0 * d.os_0 + bd_col_ofs(d, e.no);
-  } else {
-    e.o = r.obase + (long long)r.i0 * d.os_0 + bd_col_ofs(d, e.no);
-  }
-  if (d.rowbias) e.rowbias = ldg4(d.rowbias + (size_t)r.rb_row * Nout + e.no);
-  if (d.resid) e.resid = ldg4(d.resid + e.o);
-  if (d.addend) e.addend = ldg4(d.addend + e.o);
-  return e;
-}
-
-// Column-side operands of a 4-column group (bias, GroupNorm affine, LayerScale): they depend on n only,
-// so a thread that keeps its column group across rows loads them once.
+// Column-side operands of a 4-column group (bias, GroupNorm affine, LayerScale, output column offset): they
+// depend on n only, so a thread that keeps its column group across rows computes them once.
 struct EpiCol {
   float4 bias, gamma, beta, scale;
+  long long colofs;  // offset of the first stored element relative to EpiRow::obase
+  int no, nout;      // first output channel, channels per output position
+  int rr;            // transposed conv: output phase of this column group
 };
 
 __device__ __forceinline__ EpiCol bd_epi_cols4(const bd_gemm_desc& d, int n) {
@@ -116,17 +77,62 @@ __device__ __forceinline__ EpiCol bd_epi_cols4(const bd_gemm_desc& d, int n) {
     c.gamma = ldg4(d.e_gamma + n);
     c.beta = ldg4(d.e_beta + n);
   }
+  c.rr = 0;
+  if (d.act == BD_ACT_GLU) {
+    c.no = n >> 1;
+    c.nout = d.N >> 1;
+    c.colofs = bd_col_ofs(d, c.no);
+  } else if (d.convt) {
+    c.nout = d.N >> 2;
+    c.rr = n / c.nout;
+    c.no = n - c.rr * c.nout;
+    c.colofs = (long long)c.rr * d.os_0 + bd_col_ofs(d, c.no);
+  } else {
+    c.no = n;
+    c.nout = d.N;
+    c.colofs = bd_col_ofs(d, n);
+  }
   c.scale = make_float4(1.f, 1.f, 1.f, 1.f);
   if (d.resid && d.scale) {
     if (d.act == BD_ACT_GLU) {
-      const float2 t = ldg2(d.scale + (n >> 1));
+      const float2 t = ldg2(d.scale + c.no);
       c.scale.x = t.x; c.scale.y = t.y;
     } else {
-      const int no = d.convt ? n % (d.N >> 2) : n;
-      c.scale = ldg4(d.scale + no);
+      c.scale = ldg4(d.scale + c.no);
     }
   }
   return c;
+}
+
+// Memory-side operands of one 4-column group: output offset plus the residual / skip / embedding
+// values, fetched BEFORE any arithmetic so that a caller can put several groups' loads in flight
+// (the in-place residual update makes loads and stores alias, which stops the compiler from doing it).
+struct EpiMem {
+  long long o;       // output offset of the first stored element, -1: nothing to store
+  float4 resid, addend, rowbias;
+};
+
+__device__ __forceinline__ EpiMem bd_epi_fetch4(const bd_gemm_desc& d, const EpiRow& r, const EpiCol& c) {
+  EpiMem e;
+  e.resid = e.addend = e.rowbias = make_float4(0.f, 0.f, 0.f, 0.f);
+  e.o = r.obase + c.colofs;
+  if (d.convt) {
+    const int o0 = 4 * r.i0 + c.rr - (d.convt == 1 ? 2 : 0);
+    if (o0 < 0 || o0 >= d.O0) {
+      e.o = -1;
+      return e;
+    }
+  }
+  if (d.act == BD_ACT_GLU) {
+    if (d.rowbias) { const float2 t = ldg2(d.rowbias + (size_t)r.rb_row * c.nout + c.no); e.rowbias.x = t.x; e.rowbias.y = t.y; }
+    if (d.resid) { const float2 t = ldg2(d.resid + e.o); e.resid.x = t.x; e.resid.y = t.y; }
+    if (d.addend) { const float2 t = ldg2(d.addend + e.o); e.addend.x = t.x; e.addend.y = t.y; }
+    return e;
+  }
+  if (d.rowbias) e.rowbias = ldg4(d.rowbias + (size_t)r.rb_row * c.nout + c.no);
+  if (d.resid) e.resid = ldg4(d.resid + e.o);
+  if (d.addend) e.addend = ldg4(d.addend + e.o);
+  return e;
 }
 
 // Finish accumulator columns n..n+3 (n % 4 == 0, n + 3 < N) of row r.  Adds the stored values to (s, q).
@@ -167,9 +173,9 @@ __device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiR
   q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
 }
 
-__device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRow& r, const EpiCol& c, int n, float4 v,
+__device__ __forceinline__ void bd_epi_apply4(const bd_gemm_desc& d, const EpiRow& r, const EpiCol& c, float4 v,
                                               float& s, float& q) {
-  const EpiMem e = bd_epi_fetch4(d, r, n);
+  const EpiMem e = bd_epi_fetch4(d, r, c);
   bd_epi_finish4(d, r, c, v, e, s, q);
 }
 
@@ -199,9 +205,9 @@ __device__ __forceinline__ bool bd_epi_apply(const bd_gemm_desc& d, const EpiRow
     if (o0 < 0 || o0 >= d.O0) return false;
     no = n - rr * Cout;
     Nout = Cout;
-    o = r.obase + (long long)o0 * d.os_0 + bd_col_ofs(d, no);
+    o = r.obase + (long long)rr * d.os_0 + bd_col_ofs(d, no);
   } else {
-    o = r.obase + (long long)r.i0 * d.os_0 + bd_col_ofs(d, no);
+    o = r.obase + bd_col_ofs(d, no);
   }
   if (d.rowbias) v += __ldg(d.rowbias + (size_t)r.rb_row * Nout + no);
   if (d.resid) v = fmaf(d.scale ? __ldg(d.scale + no) : 1.f, v, __ldg(d.resid + o));

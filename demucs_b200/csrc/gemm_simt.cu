@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_simt_kernel(const bd_gemm_
 #pragma unroll
         for (int j = 0; j < TN; j += 4) {
           const int n = n0 + col_of(j);
-          if (n < d.N) bd_epi_apply4(d, er, ecol[j / 4], n, make_float4(acc[i][j], acc[i][(j + 1) % TN],
+          if (n < d.N) bd_epi_apply4(d, er, ecol[j / 4], make_float4(acc[i][j], acc[i][(j + 1) % TN],
                                                                         acc[i][(j + 2) % TN], acc[i][(j + 3) % TN]), rs, rq);
         }
       } else {

@@ -27,6 +27,7 @@
 // (hdemucs.py:326-334).  The stride-4 encoder convolutions, the DConv branch (HBM-bound, N or K of
 // 6..48) and C_in <= 8 layers stay on the fp32 arm (gemm_simt.cu).
 #include <cuda.h>
+#include <stdlib.h>
 #include "gemm_epilogue.cuh"
 
 namespace {
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     }
     mbar_wait_relaxed(tmem_full_bar, 0);    // also: every MMA has finished reading the smem stages
     tcgen05_fence_after();
+
     EpiRow er;
     er.obase = 0; er.i0 = 0; er.rb_row = 0; er.e_mean = 0.f; er.e_rstd = 1.f;
     if (row_ok) er = bd_epi_row(d, m);
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
           row[u].obase = ri.obase; row[u].i0 = ri.i0; row[u].rb_row = ri.rb_row;
           row[u].e_mean = ri.e_mean; row[u].e_rstd = ri.e_rstd;
           ok[u] = (it + u) * RPI < 32 && ri.i0 >= 0 && col_ok;
-          if (ok[u]) mem[u] = bd_epi_fetch4(d, row[u], n);
+          if (ok[u]) mem[u] = bd_epi_fetch4(d, row[u], ecol);
         }
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
@@ -473,6 +475,288 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
     atomicAdd(&d.stats_out[2 * (size_t)sl], red[0] + red[1] + red[2] + red[3]);
     atomicAdd(&d.stats_out[2 * (size_t)sl + 1], red[4] + red[5] + red[6] + red[7]);
   }
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---- persistent variant ----------------------------------------------------------------------------------
+// One CTA per SM walks tiles tile = blockIdx.x, blockIdx.x + gridDim.x, ...  The shared-memory ring never
+// drains between tiles, the accumulator is double-buffered in TMEM (2 x TBN columns), and the epilogue of tile i
+// (warps 4..7, dedicated staging buffer) runs while the MMA warp is already accumulating tile i+1.
+#ifndef BD_TC_EPI_GROUPS
+#define BD_TC_EPI_GROUPS 2
+#endif
+constexpr int kPGroups = BD_TC_EPI_GROUPS;                       // epilogue warps per TMEM lane quarter (column split)
+constexpr int kPThreads = 128 + 128 * kPGroups;
+
+template <int TBK, int TBN>
+struct PCfg {
+  static constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
+  static constexpr int kWarpCols = TBN / kPGroups;
+  static constexpr int kStagingBytes = 4 * kPGroups * 32 * (kWarpCols + 4) * 4;
+  static constexpr int kTailBytes = 512 + 128 * kPGroups * 32;
+  static constexpr int kBudget = 227 * 1024 - 1024 - kTailBytes - kStagingBytes;
+  static constexpr int kStagesRaw = kBudget / (kStageBytesA + kStageBytesB);
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + kStagingBytes + 1024 + kTailBytes;
+  static constexpr int kTmemCols = 2 * TBN < 32 ? 32 : 2 * TBN;
+};
+
+template <int TBK, int TBN>
+__global__ void __launch_bounds__(kPThreads, 1) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                            const __grid_constant__ CUtensorMap map_b,
+                                                                            const bd_gemm_desc d, const TileGeom g,
+                                                                            int ntiles, int ntn) {
+  using C_ = PCfg<TBK, TBN>;
+  constexpr int kStages = C_::kStages, kStageBytesA = C_::kStageBytesA, kStageBytesB = C_::kStageBytesB;
+  constexpr int kTmemCols = C_::kTmemCols;
+  constexpr int WC = C_::kWarpCols;               // columns one epilogue warp owns
+  constexpr int CW = WC < 32 ? WC : 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kStageBytesA;
+  float* staging = reinterpret_cast<float*>(sB + kStages * kStageBytesB);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + C_::kStagingBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = d.taps * g.cpb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4 * kPGroups);      // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (column block fastest, then position block, row block, item)
+  auto decode = [&](int tile, int& b, int& i0s, int& i1s, int& n0) {
+    const int nb = tile % ntn;
+    int r = tile / ntn;
+    const int blk0 = r % g.blocks0;
+    r /= g.blocks0;
+    const int blk1 = r % g.blocks1;
+    b = r / g.blocks1;
+    i0s = blk0 * g.R0;
+    i1s = blk1 * g.R1;
+    n0 = nb * TBN;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: the ring runs straight through tile boundaries =====
+    if (lane == 0) {
+      long long kbg = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int b, i0s, i1s, n0;
+        decode(tile, b, i0s, i1s, n0);
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = (int)(kbg % kStages);
+          const uint32_t ph = (uint32_t)((kbg / kStages) & 1);
+          mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
+          if (g.stride4) {
+            const int d0 = d.d0[tap];
+            tma_load_5d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, d0 & 3, i0s + (d0 >> 2), i1s + d.d1[tap], b);
+          } else {
+            tma_load_4d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, i0s + d.d0[tap], i1s + d.d1[tap], b);
+          }
+          tma_load_2d(&map_b, &full_bar[s], sB + s * kStageBytesB, tap * d.Cin + cb * TBK, n0);
+          if (++cb == g.cpb) {
+            cb = 0;
+            ++tap;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TBM, TBN);
+      long long kbg = 0;
+      int tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const int a = tcount & 1;
+        mbar_wait(&tmem_empty[a], (uint32_t)(((tcount >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(a * TBN);
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = (int)(kbg % kStages);
+          const uint32_t ph = (uint32_t)((kbg / kStages) & 1);
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint64_t adesc = make_kmajor_desc<TBK>(sA + s * kStageBytesA);
+          const uint64_t bdesc = make_kmajor_desc<TBK>(sB + s * kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < TBK / 8; ++k) umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          tcgen05_commit(&empty_bar[s]);
+        }
+        tcgen05_commit(&tmem_full[a]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 4) / 4 =====
+    const int quarter = warp & 3, grp = (warp - 4) >> 2, ew = warp - 4;
+    const int cbase = grp * WC;
+    const bool row_stats = d.stats_out && d.stat_mod != 1;
+    const bool vec = bd_epi_vec_ok(d);
+    constexpr int LDT = WC + 4;
+    float* stage = staging + (size_t)ew * 32 * LDT;
+    RowInfo* rinfo = reinterpret_cast<RowInfo*>(((uintptr_t)(tmem_slot + 4) + 31) & ~(uintptr_t)31) + ew * 32;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      int b, i0s, i1s, n0;
+      decode(tile, b, i0s, i1s, n0);
+      const int a = tcount & 1;
+      const int r = quarter * 32 + lane;
+      const int i0 = i0s + (r & (g.R0 - 1)), i1 = i1s + (r >> g.log2R0);
+      const bool row_ok = i0 < d.I0 && i1 < d.I1;
+      const long long m = ((long long)b * d.I1 + i1) * d.I0 + i0;
+      EpiRow er;
+      er.obase = 0; er.i0 = 0; er.rb_row = 0; er.e_mean = 0.f; er.e_rstd = 1.f;
+      if (row_ok) er = bd_epi_row(d, m);
+      const int my_slab = (d.stats_out && row_ok) ? bd_stat_slab(d, m) : -1;
+      float ssum = 0.f, ssq = 0.f;
+      mbar_wait_relaxed(&tmem_full[a], (uint32_t)((tcount >> 1) & 1));
+      tcgen05_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(a * TBN + cbase) + ((uint32_t)(quarter * 32) << 16);
+      if (vec) {
+        rinfo[lane].obase = er.obase;
+        rinfo[lane].i0 = row_ok ? er.i0 : -1;
+        rinfo[lane].rb_row = er.rb_row;
+        rinfo[lane].e_mean = er.e_mean;
+        rinfo[lane].e_rstd = er.e_rstd;
+        for (int c0 = 0; c0 < WC; c0 += CW) {
+          if (n0 + cbase + c0 >= d.N) break;
+          uint32_t v[CW];
+          if constexpr (CW == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+#pragma unroll
+          for (int j = 0; j < CW; j += 4)
+            *reinterpret_cast<float4*>(stage + lane * LDT + c0 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[a]);   // accumulator is free for tile i+2 while we finish tile i
+        constexpr int CG = WC / 4 < 32 ? WC / 4 : 32;
+        constexpr int RPI = 32 / CG;
+        constexpr int RB = 4;
+        const int cg = lane % CG, rsub = lane / CG;
+        const int n = n0 + cbase + 4 * cg;
+        const bool col_ok = n < d.N;
+        EpiCol ecol;
+        if (col_ok) ecol = bd_epi_cols4(d, n);
+        for (int it = 0; it < 32 / RPI; it += RB) {
+          EpiRow row[RB];
+          EpiMem mem[RB];
+          bool ok[RB];
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int rloc = (it + u) * RPI + rsub;
+            const uint32_t ra = smem_u32(&rinfo[rloc]);
+            uint32_t w0, w1, w2, w3, w4, w5;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(ra));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w4), "=r"(w5) : "r"(ra + 16));
+            row[u].obase = (long long)(((unsigned long long)w1 << 32) | w0);
+            row[u].i0 = (int)w2;
+            row[u].rb_row = (int)w3;
+            row[u].e_mean = __uint_as_float(w4);
+            row[u].e_rstd = __uint_as_float(w5);
+            ok[u] = row[u].i0 >= 0 && col_ok;
+            if (ok[u]) mem[u] = bd_epi_fetch4(d, row[u], ecol);
+          }
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int rloc = (it + u) * RPI + rsub;
+            float rs = 0.f, rq = 0.f;
+            if (ok[u]) {
+              const float4 acc4 = *reinterpret_cast<const float4*>(stage + rloc * LDT + 4 * cg);
+              bd_epi_finish4(d, row[u], ecol, acc4, mem[u], rs, rq);
+            }
+            if (row_stats) {
+              __syncwarp();
+              *reinterpret_cast<float2*>(stage + rloc * LDT + 2 * cg) = make_float2(rs, rq);
+            } else {
+              ssum += rs;
+              ssq += rq;
+            }
+          }
+        }
+        if (row_stats) {
+          __syncwarp();
+          float rs = 0.f, rq = 0.f;
+#pragma unroll
+          for (int c = 0; c < CG; ++c) {
+            const float2 t = *reinterpret_cast<const float2*>(stage + lane * LDT + 2 * c);
+            rs += t.x;
+            rq += t.y;
+          }
+          if (my_slab >= 0) {
+            atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)rs);
+            atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)rq);
+          }
+        }
+        __syncwarp();   // staging rows are rewritten by the next tile
+      } else {
+        for (int c0 = 0; c0 < WC; c0 += CW) {
+          if (n0 + cbase + c0 >= d.N) break;
+          uint32_t v[CW];
+          if constexpr (CW == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              const int n = n0 + cbase + c0 + j;
+              if (n < d.N) {
+                float st;
+                if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) % CW]), st)) {
+                  ssum += st;
+                  ssq = fmaf(st, st, ssq);
+                }
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[a]);
+        if (row_stats && row_ok) {
+          atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)ssum);
+          atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)ssq);
+        }
+      }
+      if (d.stats_out && d.stat_mod == 1) {   // one slab per tile (host guarantee): one atomic pair per warp
+        const double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
+        if (lane == 0) {
+          const int sl = bd_stat_slab(d, (long long)b * d.I1 * d.I0 + i0s);
+          atomicAdd(&d.stats_out[2 * (size_t)sl], ds);
+          atomicAdd(&d.stats_out[2 * (size_t)sl + 1], dq);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -555,6 +839,52 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
   return bd_check_launch("conv_gemm_tc_kernel");
 }
 
+template <int TBK, int TBN>
+int launch_tc_persist(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st) {
+  using C_ = PCfg<TBK, TBN>;
+  alignas(64) CUtensorMap map_a, map_b;
+  const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
+  cuuint64_t adim[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.J0, (cuuint64_t)d.J1, (cuuint64_t)items, 1};
+  cuuint64_t astr[4] = {(cuuint64_t)s0 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)sb * 4, 0};
+  cuuint32_t abox[5] = {(cuuint32_t)TBK, (cuuint32_t)g.R0, (cuuint32_t)g.R1, 1, 1};
+  int arank = 4;
+  if (g.stride4) {
+    arank = 5;
+    adim[1] = 4; adim[2] = (cuuint64_t)d.J0 / 4; adim[3] = (cuuint64_t)d.J1; adim[4] = (cuuint64_t)items;
+    astr[0] = (cuuint64_t)s0 * 4; astr[1] = (cuuint64_t)s0 * 16; astr[2] = (cuuint64_t)s1 * 4; astr[3] = (cuuint64_t)sb * 4;
+    abox[1] = 1; abox[2] = (cuuint32_t)g.R0; abox[3] = (cuuint32_t)g.R1; abox[4] = 1;
+  }
+  cuuint64_t bdim[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
+  cuuint64_t bstr[1] = {(cuuint64_t)d.K * 4};
+  cuuint32_t bbox[2] = {(cuuint32_t)TBK, (cuuint32_t)TBN};
+  if (!encode(&map_a, d.x, arank, adim, astr, abox, TBK) || !encode(&map_b, d.w, 2, bdim, bstr, bbox, TBK)) {
+    bd_set_error("bd_conv_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d Cin=%d J0=%d J1=%d)", d.M, d.N, d.K,
+                 d.Cin, d.J0, d.J1);
+    return BD_ERR_CUDA;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<TBK, TBN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes);
+    if (e != cudaSuccess) {
+      bd_set_error("bd_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return BD_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int ntn = (d.N + TBN - 1) / TBN;
+  const long long ntiles = (long long)items * g.blocks1 * g.blocks0 * ntn;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  conv_gemm_tc_persist_kernel<TBK, TBN><<<grid, kPThreads, C_::kSmemBytes, st>>>(map_a, map_b, d, g, (int)ntiles, ntn);
+  return bd_check_launch("conv_gemm_tc_persist_kernel");
+}
+
 }  // namespace
 
 // eligibility: unit-stride implicit GEMM, channels-last, big enough to fill tensor-core tiles
@@ -586,6 +916,16 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   int rc;
   const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
   const cudaStream_t st = (cudaStream_t)stream;
+  static const bool persist = getenv("BD_TC_NO_PERSIST") == nullptr;
+  if (persist && d.math != BD_MATH_TF32X3 && tbn >= 64) {   // compute-heavy tiles: persistent, overlapped epilogue
+    g.cpb = d.Cin / (d.Cin % 32 == 0 ? 32 : 16);
+    if (d.Cin % 32 == 0)
+      rc = tbn == 64 ? launch_tc_persist<32, 64>(d, g, items, st) : launch_tc_persist<32, 128>(d, g, items, st);
+    else
+      rc = tbn == 64 ? launch_tc_persist<16, 64>(d, g, items, st) : launch_tc_persist<16, 128>(d, g, items, st);
+    *handled = 1;
+    return rc;
+  }
 #define BD_TC_CASE(K_, N_) \
   if (tbn == N_) rc = x3 ? launch_tc<K_, N_, true>(d, g, items, st) : launch_tc<K_, N_, false>(d, g, items, st); else
   const bool x3 = d.math == BD_MATH_TF32X3;
