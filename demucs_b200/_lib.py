@@ -67,9 +67,11 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_layer_norm": [_P, _P, _P, _P, _P, _I, _LL, _I, _P],
     "bd_item_stats": [_P, _P, _I, _LL, _P],
     "bd_group_norm_apply": [_P, _P, _P, _P, _I, _LL, _I, _P],
+    "bd_attention_workspace": [_I, _I, _I, _I, _I],
     "bd_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "bd_overlap_add": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _LL, _P, _F, _I, _P],
 }
+VALUE_CALLS = {"bd_attention_workspace"}          # entry points that return a value, not a status
 EXPORTS = ["bd_last_error", "bd_version"] + list(SIGNATURES)
 
 _lib: tp.Optional[C.CDLL] = None
@@ -122,7 +124,7 @@ def lib() -> C.CDLL:
         handle.bd_version.restype = C.c_int
         for name, args in SIGNATURES.items():
             fn = getattr(handle, name)
-            fn.restype = C.c_int
+            fn.restype = C.c_longlong if name in VALUE_CALLS else C.c_int
             fn.argtypes = args
         _lib = handle
     return _lib
@@ -140,6 +142,13 @@ def call(name: str, *args) -> None:
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise KernelError(f"{name} failed ({rc}): {lib().bd_last_error().decode()}")
+
+
+def call_value(name: str, *args) -> int:
+    """Entry points that return a size rather than a status code."""
+    if TEST_HOOK is not None:
+        return TEST_HOOK(name, *args)
+    return int(getattr(lib(), name)(*args))
 
 
 def ptr(t) -> tp.Optional[int]:

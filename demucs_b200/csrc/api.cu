@@ -28,7 +28,8 @@ bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d);
 int bd_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
                       int ldk, int ldv, int ldo, void* stream);
 int bd_attention_tc(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
-                    int ldk, int ldv, int ldo, float* ws, void* stream);
+                    int ldk, int ldv, int ldo, int math, float* ws, void* stream);
+long long bd_attention_ws_floats(int B, int H, int Tq, int Tk, int math);
 
 extern "C" {
 
@@ -54,8 +55,14 @@ int bd_conv_gemm_arm(const bd_gemm_desc* d) {
 
 int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
                  int ldk, int ldv, int ldo, int math, float* ws, void* stream) {
-  if (math == BD_MATH_TF32) return bd_attention_tc(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, ws, stream);
+  if (math == BD_MATH_TF32 || math == BD_MATH_TF32X3)
+    return bd_attention_tc(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, math, ws, stream);
   return bd_attention_simt(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, stream);
+}
+
+long long bd_attention_workspace(int B, int H, int Tq, int Tk, int math) {
+  if (math != BD_MATH_TF32 && math != BD_MATH_TF32X3) return 0;
+  return bd_attention_ws_floats(B, H, Tq, Tk, math);
 }
 
 }  // extern "C"

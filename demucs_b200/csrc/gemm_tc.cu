@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
 // drains between tiles, the accumulator is double-buffered in TMEM (2 x TBN columns), and the epilogue of tile i
 // (warps 4..7, dedicated staging buffer) runs while the MMA warp is already accumulating tile i+1.
 #ifndef BD_TC_EPI_GROUPS
-#define BD_TC_EPI_GROUPS 2
+#define BD_TC_EPI_GROUPS 4
 #endif
 constexpr int kPGroups = BD_TC_EPI_GROUPS;                       // epilogue warps per TMEM lane quarter (column split)
 constexpr int kPThreads = 128 + 128 * kPGroups;
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_gemm_tc_persist_kernel(cons
         if (lane == 0) mbar_arrive(&tmem_empty[a]);   // accumulator is free for tile i+2 while we finish tile i
         constexpr int CG = WC / 4 < 32 ? WC / 4 : 32;
         constexpr int RPI = 32 / CG;
-        constexpr int RB = 4;
+        constexpr int RB = kPGroups >= 4 ? 2 : 4;
         const int cg = lane % CG, rsub = lane / CG;
         const int n = n0 + cbase + 4 * cg;
         const bool col_ok = n < d.N;

@@ -302,13 +302,15 @@ class Engine:
         W, D, H = self.W, self.cfg.transformer_dim, self.cfg.t_heads
         Win, bin_ = W[f"{p}.{attn}.in_proj_weight"], W[f"{p}.{attn}.in_proj_bias"]
         att = self._buf(key, f"att{tag}", B * Tq * D)
-        ws = self._buf(key, f"att_ws{tag}", B * D * ((Tk + 3) // 4 * 4)) if self.mode == "tf32" else None
+        nws = _lib.call_value("bd_attention_workspace", B, H, Tq, Tk, self._math())
+        ws = self._buf(key, f"att_ws{tag}", nws) if nws else None
+        label = "attention_simt" if self.mode == "fp32" else "attention_tc"
         if kv_src is None:  # self attention: one packed projection
             qkv = self._buf(key, f"qkv{tag}", B * Tq * 3 * D)
             self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv)
             self._k("bd_attention", ptr(qkv), qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, ptr(att),
                     B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), ptr(ws), self._stream(),
-                    flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label="attention_tc" if self.mode == "tf32" else "attention_simt")
+                    flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label=label)
         else:
             q = self._buf(key, f"q{tag}", B * Tq * D)
             kv = self._buf(key, f"kv{tag}", B * Tk * 2 * D)
@@ -316,13 +318,13 @@ class Engine:
             self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv)
             self._k("bd_attention", ptr(q), ptr(kv), kv.data_ptr() + 4 * D, ptr(att),
                     B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), ptr(ws), self._stream(),
-                    flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label="attention_tc" if self.mode == "tf32" else "attention_simt")
+                    flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label=label)
         return att
 
     def _math(self) -> int:
-        """Arithmetic of the attention core: tcgen05 in "tf32" mode, exact fp32 otherwise (the
-        error-compensated mode keeps the softmax path in fp32)."""
-        return _lib.MATH_TF32 if self.mode == "tf32" else _lib.MATH_FP32
+        """Arithmetic of the attention core: tcgen05 in both tensor-core modes (three-pass hi/lo products in
+        "tf32x3"), CUDA cores in "fp32"."""
+        return {"tf32": _lib.MATH_TF32, "tf32x3": _lib.MATH_TF32X3}.get(self.mode, _lib.MATH_FP32)
 
     def _ln(self, x, y, p: str, M: int, pos=None, period=0):
         D = self.cfg.transformer_dim

@@ -150,7 +150,9 @@ int bd_group_norm_apply(float* x, const float* mean_rstd, const float* gamma, co
 
 /* K6 (nn.MultiheadAttention via _sa_block/_ca_block, transformer.py:365,418,506): softmax(QK^T/8)V,
  * head_dim 64, no mask.  q [B,Tq,ldq] / k,v [B,Tk,ldk] / o [B,Tq,ldo]; head h uses columns [64h, 64h+64). */
-/* ws: workspace of B*H*64*ceil4(Tk) floats for the BD_MATH_TF32 arm (V^T staging), may be NULL otherwise. */
+/* ws: workspace of bd_attention_workspace(...) floats for the tensor-core arms (V^T staging; hi/lo operand
+ * splits for BD_MATH_TF32X3), may be NULL when that is 0 (BD_MATH_FP32). */
+long long bd_attention_workspace(int B, int H, int Tq, int Tk, int math);
 int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk,
                  int ldq, int ldk, int ldv, int ldo, int math, float* ws, void* stream);
 

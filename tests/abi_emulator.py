@@ -250,6 +250,15 @@ def _strided(p, B, T, ld, ncol):
     return np.lib.stride_tricks.as_strided(a, shape=(B, T, ncol), strides=(T * ld * 4, ld * 4, 4))
 
 
+def bd_attention_workspace(B, H, Tq, Tk, math_):
+    D, Tkp = 64 * H, (Tk + 3) // 4 * 4
+    if math_ == _lib.MATH_TF32:
+        return B * D * Tkp
+    if math_ == _lib.MATH_TF32X3:
+        return 2 * B * D * (Tkp + Tq + Tk)
+    return 0
+
+
 def bd_attention(q, k, v, o, B, H, Tq, Tk, ldq, ldk, ldv, ldo, math_, ws, stream):
     D = 64 * H
     qv, kv, vv = _strided(q, B, Tq, ldq, D), _strided(k, B, Tk, ldk, D), _strided(v, B, Tk, ldv, D)
@@ -294,7 +303,7 @@ CALLS = []
 def hook(name, *args):
     CALLS.append(name)
     args = [a.value if isinstance(a, C.c_void_p) else a for a in args]
-    TABLE[name](*args)
+    return TABLE[name](*args)
 
 
 @contextlib.contextmanager
