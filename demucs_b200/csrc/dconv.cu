@@ -192,14 +192,259 @@ int launch_expand(const float* h, int ldh, int hid, const float* mr1, const floa
 #undef BD_DC_ARGS
 }
 
+
+// ---- pass 1 through the Gram matrix ---------------------------------------------------------------------
+// sum(u) and sum(u^2) over a slab are quadratic forms of the slab's g statistics:
+//     sum_rows sum_n u_n   = sum_n (w_n . sg) + R sum_n b_n                    sg = sum_rows g
+//     sum_rows sum_n u_n^2 = sum_n (w_n^T G w_n + 2 b_n (w_n . sg) + R b_n^2)   G  = sum_rows g g^T
+// so pass 1 needs hid^2 products per row instead of hid * 2C (16x fewer) and never forms u at all.
+// A warp walks rows r = (c*K + k)*P + 32*sb + lane of one item, P = max(32, slabs_per_item): the slab of a lane
+// is the same in every iteration, lanes that share a slab (slabs_per_item < 32) are folded with shuffles, and
+// each slab's owner lane adds its BLK x BLK block of G (and sg) to the fp64 workspace.
+template <int BLK>
+__global__ void __launch_bounds__(256, (BLK <= 8 ? 2 : 1)) dconv_gram_kernel(const float* __restrict__ h, int ldh, int hid,
+                                                         const float* __restrict__ mr1, const float* __restrict__ g1,
+                                                         const float* __restrict__ be1, double* __restrict__ gram,
+                                                         long long rpi, int spi, int items, int K, int ngroups) {
+  constexpr int NACC = BLK * BLK + BLK, LDA = NACC | 1;       // odd pitch: lanes hit different banks
+  __shared__ float buf[32 * LDA];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = hid / BLK, nunits = nblk * (nblk + 1) / 2;
+  const int P = spi > 32 ? spi : 32, nsb = P / 32;
+  const int nown = spi < 32 ? spi : 32;                       // lanes that own a slab after the fold
+  const long long nwork = (long long)items * nunits * nsb * ngroups;
+  const int GS = hid * hid + hid;
+  // CTA = 8 warps = 8 consecutive row chunks of one (item, block pair, slab block): their partial sums meet in
+  // shared memory, so the fp64 workspace sees one atomic per value and CTA instead of one per warp
+  for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    long long t = wk;
+    const int c = (int)(t % ngroups) * 8 + warp; t /= ngroups;
+    const int sb = (int)(t % nsb); t /= nsb;
+    int unit = (int)(t % nunits);
+    const int item = (int)(t / nunits);
+    int bi = 0;
+    while (unit >= nblk - bi) { unit -= nblk - bi; ++bi; }
+    const int bj = bi + unit;
+    const bool diag = bi == bj;
+    for (int i = threadIdx.x; i < 32 * LDA; i += 256) buf[i] = 0.f;
+    __syncthreads();
+    float ga[BLK], bea[BLK], gb[BLK], beb[BLK];
+#pragma unroll
+    for (int a = 0; a < BLK; ++a) {
+      ga[a] = __ldg(g1 + bi * BLK + a); bea[a] = __ldg(be1 + bi * BLK + a);
+      gb[a] = __ldg(g1 + bj * BLK + a); beb[a] = __ldg(be1 + bj * BLK + a);
+    }
+    float acc[BLK][BLK], sg[BLK];
+#pragma unroll
+    for (int a = 0; a < BLK; ++a) {
+      sg[a] = 0.f;
+#pragma unroll
+      for (int b = 0; b < BLK; ++b) acc[a][b] = 0.f;
+    }
+    const long long r_first = (long long)c * K * P + 32 * sb + lane;
+    const int s_lane = (int)((32LL * sb + lane) % spi);
+    const long long slab = (long long)item * spi + s_lane;
+    const float mean1 = __ldg(mr1 + 2 * slab), rstd1 = __ldg(mr1 + 2 * slab + 1);
+    // rows in batches of UB with every load issued before the first GELU (the chain load -> erf -> fma is long)
+    constexpr int UB = BLK > 8 ? 2 : 4;
+    for (int k0 = 0; k0 < K; k0 += UB) {
+      if (r_first - lane + (long long)k0 * P >= rpi) break;     // warp-uniform
+      float ra[UB][BLK], rb[UB][BLK];
+      bool live[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const long long r = r_first + (long long)(k0 + u) * P;
+        live[u] = k0 + u < K && r < rpi;
+        const float* hr = h + ((long long)item * rpi + (live[u] ? r : 0)) * ldh;
+        if (BLK % 4 == 0) {
+#pragma unroll
+          for (int a = 0; a < BLK; a += 4) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(hr + bi * BLK + a));
+            ra[u][a] = q0.x; ra[u][a + 1] = q0.y; ra[u][a + 2] = q0.z; ra[u][a + 3] = q0.w;
+            if (!diag) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(hr + bj * BLK + a));
+              rb[u][a] = q.x; rb[u][a + 1] = q.y; rb[u][a + 2] = q.z; rb[u][a + 3] = q.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < BLK; a += 2) {
+            const float2 q0 = __ldg(reinterpret_cast<const float2*>(hr + bi * BLK + a));
+            ra[u][a] = q0.x; ra[u][a + 1] = q0.y;
+            if (!diag) {
+              const float2 q = __ldg(reinterpret_cast<const float2*>(hr + bj * BLK + a));
+              rb[u][a] = q.x; rb[u][a + 1] = q.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (!live[u]) continue;
+        float va[BLK], vb[BLK];
+#pragma unroll
+        for (int a = 0; a < BLK; ++a) {
+          va[a] = bd_gelu(fmaf((ra[u][a] - mean1) * rstd1, ga[a], bea[a]));
+          sg[a] += va[a];
+        }
+        if (diag) {
+#pragma unroll
+          for (int a = 0; a < BLK; ++a) vb[a] = va[a];
+        } else {
+#pragma unroll
+          for (int a = 0; a < BLK; ++a) vb[a] = bd_gelu(fmaf((rb[u][a] - mean1) * rstd1, gb[a], beb[a]));
+        }
+#pragma unroll
+        for (int a = 0; a < BLK; ++a)
+#pragma unroll
+          for (int b = 0; b < BLK; ++b) acc[a][b] = fmaf(va[a], vb[b], acc[a][b]);
+      }
+    }
+    // fold lanes that share a slab, then meet the other warps in shared memory
+    for (int o = 16; o >= spi; o >>= 1) {
+#pragma unroll
+      for (int a = 0; a < BLK; ++a) {
+        sg[a] += __shfl_xor_sync(0xffffffffu, sg[a], o);
+#pragma unroll
+        for (int b = 0; b < BLK; ++b) acc[a][b] += __shfl_xor_sync(0xffffffffu, acc[a][b], o);
+      }
+    }
+    if (lane < nown && r_first - lane < rpi) {
+#pragma unroll
+      for (int a = 0; a < BLK; ++a) {
+#pragma unroll
+        for (int b = 0; b < BLK; ++b) atomicAdd(&buf[lane * LDA + a * BLK + b], acc[a][b]);
+        atomicAdd(&buf[lane * LDA + BLK * BLK + a], sg[a]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nown * NACC; i += 256) {
+      const int ln = i / NACC, idx = i - ln * NACC;
+      const long long sl = (long long)item * spi + (32LL * sb + ln) % spi;
+      double* G = gram + sl * GS;
+      const float v = buf[ln * LDA + idx];
+      if (idx < BLK * BLK) {
+        const int a = idx / BLK, b2 = idx - a * BLK;
+        atomicAdd(&G[(bi * BLK + a) * hid + bj * BLK + b2], (double)v);
+      } else if (diag) {
+        atomicAdd(&G[hid * hid + bi * BLK + idx - BLK * BLK], (double)v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// The column sums of the quadratic forms depend on the weights only:
+//     sum_n w_n^T G w_n = sum_ab G[a][b] WW[a][b],   WW = W2^T W2;   sum_n b_n (w_n . sg) = wb . sg;   ...
+// wst = [WW (hid*hid) | ws = sum_n w_n (hid) | wb = sum_n b_n w_n (hid) | sum b_n | sum b_n^2], one warp per
+// entry.  The same launch clears the Gram workspace.
+__global__ void __launch_bounds__(256) dconv_wstats_kernel(const float* __restrict__ w2t, const float* __restrict__ b2, int hid,
+                                                           int N, double* __restrict__ wst, double* __restrict__ gram,
+                                                           long long gram_count) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < gram_count; i += (long long)gridDim.x * 256) gram[i] = 0.0;
+  const int lane = threadIdx.x & 31;
+  const int E = hid * hid + 2 * hid + 2;
+  for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < E; e += gridDim.x * 8) {
+    double acc = 0.0;
+    for (int n = lane; n < N; n += 32) {
+      double x, y;
+      if (e < hid * hid) {
+        x = (double)__ldg(w2t + (size_t)(e / hid) * N + n);
+        y = (double)__ldg(w2t + (size_t)(e % hid) * N + n);
+      } else if (e < hid * hid + hid) {
+        x = (double)__ldg(w2t + (size_t)(e - hid * hid) * N + n);
+        y = 1.0;
+      } else if (e < hid * hid + 2 * hid) {
+        x = (double)__ldg(w2t + (size_t)(e - hid * hid - hid) * N + n);
+        y = (double)__ldg(b2 + n);
+      } else {
+        x = (double)__ldg(b2 + n);
+        y = e == hid * hid + 2 * hid ? 1.0 : x;
+      }
+      acc = fma(x, y, acc);
+    }
+    acc = bd_warp_sum_d(acc);
+    if (lane == 0) wst[e] = acc;
+  }
+}
+
+// sums2[slab] += (sum u, sum u^2) from the slab's Gram matrix: one warp per slab
+template <int BLK>
+__global__ void __launch_bounds__(256) dconv_gram_eval_kernel(const double* __restrict__ gram, const double* __restrict__ wst,
+                                                              int hid, double* __restrict__ sums2, long long slabs, double R) {
+  const int lane = threadIdx.x & 31;
+  const long long slab = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (slab >= slabs) return;
+  const int HH = hid * hid, GS = HH + hid;
+  const double* G = gram + slab * GS;
+  double S = 0.0, Q = 0.0;
+  for (int i = lane; i < HH; i += 32) {
+    const int a = i / hid, b = i - a * hid;
+    const double g = (a / BLK <= b / BLK) ? G[i] : G[b * hid + a];   // only blocks with bi <= bj were accumulated
+    Q = fma(g, wst[i], Q);
+  }
+  for (int a = lane; a < hid; a += 32) {
+    const double sg = G[HH + a];
+    S = fma(wst[HH + a], sg, S);
+    Q = fma(2.0 * wst[HH + hid + a], sg, Q);
+  }
+  S = bd_warp_sum_d(S);
+  Q = bd_warp_sum_d(Q);
+  if (lane == 0) {
+    sums2[2 * slab] += S + R * wst[HH + 2 * hid];
+    sums2[2 * slab + 1] += Q + R * wst[HH + 2 * hid + 1];
+  }
+}
+
+bool gram_supported(int hid, int ldh, long long rpi, int spi) {
+  if (hid != 6 && hid != 12 && hid != 24 && hid != 48) return false;
+  if (ldh % (hid == 6 ? 2 : 4) != 0) return false;             // vector loads of the h rows
+  if (spi <= 0 || rpi % spi != 0) return false;
+  return spi >= 32 ? spi % 32 == 0 : 32 % spi == 0;
+}
+
+template <int HID, int BLK>
+int launch_gram(const float* h, int ldh, int hid, const float* mr1, const float* g1, const float* be1, const float* w2t,
+                const float* b2, double* sums2, double* gram, long long M, int C, long long rpi, int spi, cudaStream_t st) {
+  const int items = (int)(M / rpi);
+  const long long slabs = (long long)items * spi;
+  const int GS = hid * hid + hid;
+  double* wst = gram + slabs * GS;                            // weight-only sums live behind the Gram matrices
+  dconv_wstats_kernel<<<148, 256, 0, st>>>(w2t, b2, hid, 2 * C, wst, gram, slabs * GS);
+  if (bd_check_launch("dconv_wstats_kernel") != BD_OK) return BD_ERR_CUDA;
+  const int P = spi > 32 ? spi : 32, nsb = P / 32, nblk = hid / BLK, nunits = nblk * (nblk + 1) / 2;
+  const long long periods = (rpi + P - 1) / P;               // iterations needed to cover an item
+  // enough CTAs (8 warps each) to fill the machine, at least 8 rows per lane to amortise the reduction
+  const long long base = (long long)items * nunits * nsb;
+  long long ngroups = (148LL * 4 + base - 1) / base;
+  if (ngroups > (periods + 63) / 64) ngroups = (periods + 63) / 64;
+  if (ngroups < 1) ngroups = 1;
+  const int K = (int)((periods + 8 * ngroups - 1) / (8 * ngroups));
+  ngroups = (periods + 8LL * K - 1) / (8LL * K);
+  long long grid = base * ngroups;
+  if (grid > 148LL * 8) grid = 148LL * 8;
+  dconv_gram_kernel<BLK><<<(unsigned)grid, 256, 0, st>>>(h, ldh, hid, mr1, g1, be1, gram, rpi, spi, items, K, (int)ngroups);
+  if (bd_check_launch("dconv_gram_kernel") != BD_OK) return BD_ERR_CUDA;
+  dconv_gram_eval_kernel<BLK><<<(unsigned)((slabs + 7) / 8), 256, 0, st>>>(gram, wst, hid, sums2, slabs, (double)(rpi / spi));
+  return bd_check_launch("dconv_gram_eval_kernel");
+}
+
 }  // namespace
 
 extern "C" {
 
 int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
-                          const float* beta1, const float* w2t, const float* b2, double* sums2, long long M, int C,
-                          long long rows_per_item, int slabs_per_item, void* stream) {
+                          const float* beta1, const float* w2t, const float* b2, double* sums2, double* gram_ws,
+                          long long M, int C, long long rows_per_item, int slabs_per_item, void* stream) {
   BD_REQUIRE(hid > 0 && hid <= MAX_HID && C % 2 == 0 && ldh >= hid && M > 0, "bd_dconv_expand_stats: bad sizes (hid=%d C=%d)", hid, C);
+  if (gram_ws && M % rows_per_item == 0 && gram_supported(hid, ldh, rows_per_item, slabs_per_item)) {
+#define BD_GRAM_ARGS h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, sums2, gram_ws, M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream
+    if (hid == 6) return launch_gram<6, 6>(BD_GRAM_ARGS);
+    if (hid == 12) return launch_gram<12, 12>(BD_GRAM_ARGS);
+    if (hid == 24) return launch_gram<24, 12>(BD_GRAM_ARGS);
+    return launch_gram<48, 12>(BD_GRAM_ARGS);
+#undef BD_GRAM_ARGS
+  }
   return launch_expand<false>(h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, sums2, nullptr, nullptr, nullptr, nullptr,
                               nullptr, M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream);
 }

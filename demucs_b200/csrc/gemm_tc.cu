@@ -488,12 +488,16 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
 #ifndef BD_TC_EPI_GROUPS
 #define BD_TC_EPI_GROUPS 4
 #endif
-constexpr int kPGroups = BD_TC_EPI_GROUPS;                       // epilogue warps per TMEM lane quarter (column split)
-constexpr int kPThreads = 128 + 128 * kPGroups;
-
-template <int TBK, int TBN>
+// Epilogue warps per TMEM lane quarter (column split): 4 in the single-pass kernel, where the epilogue is the
+// bottleneck; the 3xTF32 kernel spends 3x longer per tile on the tensor core, so 2 suffice and 4 more warps
+// split the fp32 operand tiles into tf32 hi / lo parts in shared memory.
+template <int TBK, int TBN, bool X3>
 struct PCfg {
-  static constexpr int kStageBytesA = TBM * TBK * 4, kStageBytesB = TBN * TBK * 4;
+  static constexpr int kPGroups = X3 ? 2 : BD_TC_EPI_GROUPS;
+  static constexpr int kEpiWarp0 = X3 ? 8 : 4;       // warps 0 TMA, 1 MMA, (4..7 splitters), then epilogue
+  static constexpr int kThreads = 32 * kEpiWarp0 + 128 * kPGroups;
+  static constexpr int kTileBytesA = TBM * TBK * 4, kTileBytesB = TBN * TBK * 4;
+  static constexpr int kStageBytesA = (X3 ? 2 : 1) * kTileBytesA, kStageBytesB = (X3 ? 2 : 1) * kTileBytesB;
   static constexpr int kWarpCols = TBN / kPGroups;
   static constexpr int kStagingBytes = 4 * kPGroups * 32 * (kWarpCols + 4) * 4;
   static constexpr int kTailBytes = 512 + 128 * kPGroups * 32;
@@ -504,12 +508,14 @@ struct PCfg {
   static constexpr int kTmemCols = 2 * TBN < 32 ? 32 : 2 * TBN;
 };
 
-template <int TBK, int TBN>
-__global__ void __launch_bounds__(kPThreads, 1) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
+template <int TBK, int TBN, bool X3>
+__global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                             const __grid_constant__ CUtensorMap map_b,
                                                                             const bd_gemm_desc d, const TileGeom g,
                                                                             int ntiles, int ntn) {
-  using C_ = PCfg<TBK, TBN>;
+  using C_ = PCfg<TBK, TBN, X3>;
+  constexpr int kPGroups = C_::kPGroups;
+  constexpr int kTileBytesA = C_::kTileBytesA, kTileBytesB = C_::kTileBytesB;
   constexpr int kStages = C_::kStages, kStageBytesA = C_::kStageBytesA, kStageBytesB = C_::kStageBytesB;
   constexpr int kTmemCols = C_::kTmemCols;
   constexpr int WC = C_::kWarpCols;               // columns one epilogue warp owns
@@ -523,7 +529,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_gemm_tc_persist_kernel(cons
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;       // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* conv_bar = tmem_empty + 2;             // [kStages] X3: hi/lo tiles written by the splitter warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = d.taps * g.cpb;
@@ -532,6 +539,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_gemm_tc_persist_kernel(cons
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 128);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_gemm_tc_persist_kernel(cons
           const int s = (int)(kbg % kStages);
           const uint32_t ph = (uint32_t)((kbg / kStages) & 1);
           mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
+          mbar_expect_tx(&full_bar[s], kTileBytesA + kTileBytesB);
           if (g.stride4) {
             const int d0 = d.d0[tap];
             tma_load_5d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, d0 & 3, i0s + (d0 >> 2), i1s + d.d1[tap], b);
@@ -603,20 +611,55 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_gemm_tc_persist_kernel(cons
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = (int)(kbg % kStages);
           const uint32_t ph = (uint32_t)((kbg / kStages) & 1);
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], ph);
           tcgen05_fence_after();
           const uint64_t adesc = make_kmajor_desc<TBK>(sA + s * kStageBytesA);
           const uint64_t bdesc = make_kmajor_desc<TBK>(sB + s * kStageBytesB);
 #pragma unroll
-          for (int k = 0; k < TBK / 8; ++k) umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < TBK / 8; ++k) {
+            if constexpr (X3) {
+              const uint64_t alo = make_kmajor_desc<TBK>(sA + s * kStageBytesA + kTileBytesA);
+              const uint64_t blo = make_kmajor_desc<TBK>(sB + s * kStageBytesB + kTileBytesB);
+              umma_tf32(acc, alo + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);   // small terms first
+              umma_tf32(acc, adesc + 2 * k, blo + 2 * k, idesc, 1);
+              umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            } else {
+              umma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+          }
           tcgen05_commit(&empty_bar[s]);
         }
         tcgen05_commit(&tmem_full[a]);
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 4) / 4 =====
-    const int quarter = warp & 3, grp = (warp - 4) >> 2, ew = warp - 4;
+  } else if (X3 && warp >= 4 && warp < 8) {
+    // ===== operand splitter (3xTF32): x -> tf32(x) in place, x - tf32(x) into the lo half of the stage =====
+    const int et = threadIdx.x - 128;      // 0..127
+    long long kbg = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+        const int s = (int)(kbg % kStages);
+        mbar_wait(&full_bar[s], (uint32_t)((kbg / kStages) & 1));
+        auto split = [&](uint8_t* base, int tile_bytes) {
+          float4* hi = reinterpret_cast<float4*>(base);
+          float4* lo = reinterpret_cast<float4*>(base + tile_bytes);
+#pragma unroll 4
+          for (int i = et; i < tile_bytes / 16; i += 128) {
+            const float4 x = hi[i];
+            const float4 h = make_float4(rn_tf32(x.x), rn_tf32(x.y), rn_tf32(x.z), rn_tf32(x.w));
+            hi[i] = h;
+            lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          }
+        };
+        split(sA + s * kStageBytesA, kTileBytesA);
+        split(sB + s * kStageBytesB, kTileBytesB);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> UMMA reads
+        mbar_arrive(&conv_bar[s]);
+      }
+    }
+  } else if (warp >= C_::kEpiWarp0) {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - first) / 4 =====
+    const int quarter = warp & 3, ew = warp - C_::kEpiWarp0, grp = ew >> 2;
     const int cbase = grp * WC;
     const bool row_stats = d.stats_out && d.stat_mod != 1;
     const bool vec = bd_epi_vec_ok(d);
@@ -839,9 +882,9 @@ int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t 
   return bd_check_launch("conv_gemm_tc_kernel");
 }
 
-template <int TBK, int TBN>
+template <int TBK, int TBN, bool X3>
 int launch_tc_persist(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st) {
-  using C_ = PCfg<TBK, TBN>;
+  using C_ = PCfg<TBK, TBN, X3>;
   alignas(64) CUtensorMap map_a, map_b;
   const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
   cuuint64_t adim[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.J0, (cuuint64_t)d.J1, (cuuint64_t)items, 1};
@@ -864,7 +907,7 @@ int launch_tc_persist(const bd_gemm_desc& d, const TileGeom& g, int items, cudaS
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<TBK, TBN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<TBK, TBN, X3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes);
     if (e != cudaSuccess) {
       bd_set_error("bd_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -881,7 +924,7 @@ int launch_tc_persist(const bd_gemm_desc& d, const TileGeom& g, int items, cudaS
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  conv_gemm_tc_persist_kernel<TBK, TBN><<<grid, kPThreads, C_::kSmemBytes, st>>>(map_a, map_b, d, g, (int)ntiles, ntn);
+  conv_gemm_tc_persist_kernel<TBK, TBN, X3><<<grid, C_::kThreads, C_::kSmemBytes, st>>>(map_a, map_b, d, g, (int)ntiles, ntn);
   return bd_check_launch("conv_gemm_tc_persist_kernel");
 }
 
@@ -917,12 +960,17 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
   const cudaStream_t st = (cudaStream_t)stream;
   static const bool persist = getenv("BD_TC_NO_PERSIST") == nullptr;
-  if (persist && d.math != BD_MATH_TF32X3 && tbn >= 64) {   // compute-heavy tiles: persistent, overlapped epilogue
-    g.cpb = d.Cin / (d.Cin % 32 == 0 ? 32 : 16);
-    if (d.Cin % 32 == 0)
-      rc = tbn == 64 ? launch_tc_persist<32, 64>(d, g, items, st) : launch_tc_persist<32, 128>(d, g, items, st);
-    else
-      rc = tbn == 64 ? launch_tc_persist<16, 64>(d, g, items, st) : launch_tc_persist<16, 128>(d, g, items, st);
+  if (persist && tbn >= 64) {   // compute-heavy tiles: persistent, overlapped epilogue
+    if (d.math == BD_MATH_TF32X3) {   // hi/lo stages are twice the size: 16-wide k-blocks keep 4 of them
+      g.cpb = d.Cin / 16;
+      rc = tbn == 64 ? launch_tc_persist<16, 64, true>(d, g, items, st) : launch_tc_persist<16, 128, true>(d, g, items, st);
+    } else if (d.Cin % 32 == 0) {
+      g.cpb = d.Cin / 32;
+      rc = tbn == 64 ? launch_tc_persist<32, 64, false>(d, g, items, st) : launch_tc_persist<32, 128, false>(d, g, items, st);
+    } else {
+      g.cpb = d.Cin / 16;
+      rc = tbn == 64 ? launch_tc_persist<16, 64, false>(d, g, items, st) : launch_tc_persist<16, 128, false>(d, g, items, st);
+    }
     *handled = 1;
     return rc;
   }

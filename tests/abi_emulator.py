@@ -205,7 +205,7 @@ def _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi):
     return u.astype(np.float32), slab
 
 
-def bd_dconv_expand_stats(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, M, Cc, rpi, spi, stream):
+def bd_dconv_expand_stats(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, gram_ws, M, Cc, rpi, spi, stream):
     u, slab = _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi)
     st = f64(sums2, 2 * (int(slab.max()) + 1)).reshape(-1, 2)
     u64 = u.astype(np.float64)
