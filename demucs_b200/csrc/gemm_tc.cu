@@ -102,6 +102,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > kSpinLimit) __trap();
   }
 }
+// Single-thread roles (TMA producer, MMA issuer) in the persistent kernel: let the hardware park the thread for
+// up to ~1 us per poll instead of spinning through the issue slots the epilogue warps need.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000)
+        : "memory");
+    if (done) return;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
 // Same, for waiters that are not on the critical path (epilogue warps parked during the main loop, the
 // producer waiting for a free stage): back off between polls so that they do not compete for issue slots.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
@@ -481,6 +497,129 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_con
   }
 }
 
+// ---- lean epilogue for the common layer shapes -----------------------------------------------------------
+// The generic bd_epi_* helpers test every optional operand per 4-column group; for the layers that dominate the
+// run time (plain / GELU / GLU, optional GroupNorm affine, optional LayerScale residual; no transposed-conv
+// scatter, channel split, row bias or addend) this version fixes the combination at compile time, keeps
+// everything in 32-bit shared-space addresses and predicates instead of branching on row / column validity.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.44269504088896340736f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
+template <int ACT, bool E, bool RES, int WC, int RB>
+__device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t stage_s, uint32_t rinfo_s, int lane, int n0w,
+                                              float& ssum, float& ssq) {
+  constexpr int LDT = WC + 4;
+  constexpr int CG = WC / 4 < 32 ? WC / 4 : 32;   // lanes across the warp's columns
+  constexpr int RPI = 32 / CG;                    // rows per pass
+  const int cg = lane % CG, rsub = lane / CG;
+  const int n = n0w + 4 * cg;
+  const bool col_ok = n < d.N;
+  const int nc = col_ok ? n : 0;                  // clamped: operands are fetched unconditionally
+  const float4 bias = d.bias ? ldg4(d.bias + nc) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (E) {
+    gam = ldg4(d.e_gamma + nc);
+    bet = ldg4(d.e_beta + nc);
+  }
+  const int no = ACT == BD_ACT_GLU ? nc >> 1 : nc;
+  float4 scl = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (RES && d.scale) {
+    if (ACT == BD_ACT_GLU) {
+      const float2 t = ldg2(d.scale + no);
+      scl.x = t.x; scl.y = t.y;
+    } else {
+      scl = ldg4(d.scale + no);
+    }
+  }
+  float* outp = d.out + no;
+  const float* resp = RES ? d.resid + no : nullptr;
+  const uint32_t st_lane = stage_s + (uint32_t)(rsub * LDT + 4 * cg) * 4u;
+  const uint32_t ri_lane = rinfo_s + (uint32_t)rsub * 32u;
+#pragma unroll 1
+  for (int it = 0; it < 32 / RPI; it += RB) {
+    long long ob[RB];
+    bool ok[RB];
+    float mean[RB], rstd[RB];
+    float4 res[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const uint32_t ra = ri_lane + (uint32_t)((it + u) * RPI) * 32u;
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(ra));
+      ob[u] = (long long)(((unsigned long long)w1 << 32) | w0);
+      ok[u] = (int)w2 >= 0 && col_ok;
+      if (E) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mean[u]), "=f"(rstd[u]) : "r"(ra + 16));
+      if (RES) {
+        res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[u]) {
+          if (ACT == BD_ACT_GLU) {
+            const float2 t = ldg2(resp + ob[u]);
+            res[u].x = t.x; res[u].y = t.y;
+          } else {
+            res[u] = ldg4(resp + ob[u]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      float4 v = lds128(st_lane + (uint32_t)((it + u) * RPI * LDT) * 4u);
+      v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+      if (E) {
+        v.x = fmaf((v.x - mean[u]) * rstd[u], gam.x, bet.x);
+        v.y = fmaf((v.y - mean[u]) * rstd[u], gam.y, bet.y);
+        v.z = fmaf((v.z - mean[u]) * rstd[u], gam.z, bet.z);
+        v.w = fmaf((v.w - mean[u]) * rstd[u], gam.w, bet.w);
+      }
+      if (ACT == BD_ACT_GLU) {
+        float2 o2 = make_float2(v.x * sigmoid_fast(v.y), v.z * sigmoid_fast(v.w));
+        if (RES) {
+          o2.x = fmaf(scl.x, o2.x, res[u].x);
+          o2.y = fmaf(scl.y, o2.y, res[u].y);
+        }
+        if (ok[u]) {
+          *reinterpret_cast<float2*>(outp + ob[u]) = o2;
+          ssum += o2.x + o2.y;
+          ssq = fmaf(o2.x, o2.x, fmaf(o2.y, o2.y, ssq));
+        }
+      } else {
+        if (ACT == BD_ACT_GELU) {
+          v.x = bd_gelu(v.x); v.y = bd_gelu(v.y); v.z = bd_gelu(v.z); v.w = bd_gelu(v.w);
+        }
+        if (RES) {
+          v.x = fmaf(scl.x, v.x, res[u].x); v.y = fmaf(scl.y, v.y, res[u].y);
+          v.z = fmaf(scl.z, v.z, res[u].z); v.w = fmaf(scl.w, v.w, res[u].w);
+        }
+        if (ok[u]) {
+          *reinterpret_cast<float4*>(outp + ob[u]) = v;
+          ssum += (v.x + v.y) + (v.z + v.w);
+          ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
+        }
+      }
+    }
+  }
+}
+
+// which compile-time combination (if any) covers this launch; uniform per kernel
+__device__ __forceinline__ int epi_fast_id(const bd_gemm_desc& d, bool vec, bool row_stats) {
+  if (!vec || row_stats || !d.out || d.convt || d.oc_split || d.rowbias || d.addend) return -1;
+  const bool e = d.e_stats != nullptr, r = d.resid != nullptr;
+  if (d.act == BD_ACT_NONE && !e) return r ? 1 : 0;
+  if (d.act == BD_ACT_GELU && !e && !r) return 2;
+  if (d.act == BD_ACT_GLU && !e && !r) return 3;
+  if (d.act == BD_ACT_GLU && e && r) return 4;
+  return -1;
+}
+
 // ---- persistent variant ----------------------------------------------------------------------------------
 // One CTA per SM walks tiles tile = blockIdx.x, blockIdx.x + gridDim.x, ...  The shared-memory ring never
 // drains between tiles, the accumulator is double-buffered in TMEM (2 x TBN columns), and the epilogue of tile i
@@ -581,7 +720,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = (int)(kbg % kStages);
           const uint32_t ph = (uint32_t)((kbg / kStages) & 1);
-          mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
+          mbar_wait_parked(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], kTileBytesA + kTileBytesB);
           if (g.stride4) {
             const int d0 = d.d0[tap];
@@ -605,13 +744,13 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
       int tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         const int a = tcount & 1;
-        mbar_wait(&tmem_empty[a], (uint32_t)(((tcount >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
+        mbar_wait_parked(&tmem_empty[a], (uint32_t)(((tcount >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(a * TBN);
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = (int)(kbg % kStages);
           const uint32_t ph = (uint32_t)((kbg / kStages) & 1);
-          mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], ph);
+          mbar_wait_parked(X3 ? &conv_bar[s] : &full_bar[s], ph);
           tcgen05_fence_after();
           const uint64_t adesc = make_kmajor_desc<TBK>(sA + s * kStageBytesA);
           const uint64_t bdesc = make_kmajor_desc<TBK>(sB + s * kStageBytesB);
@@ -663,6 +802,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
     const int cbase = grp * WC;
     const bool row_stats = d.stats_out && d.stat_mod != 1;
     const bool vec = bd_epi_vec_ok(d);
+    const int fast = epi_fast_id(d, vec, row_stats);
     constexpr int LDT = WC + 4;
     float* stage = staging + (size_t)ew * 32 * LDT;
     RowInfo* rinfo = reinterpret_cast<RowInfo*>(((uintptr_t)(tmem_slot + 4) + 31) & ~(uintptr_t)31) + ew * 32;
@@ -677,7 +817,17 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
       const long long m = ((long long)b * d.I1 + i1) * d.I0 + i0;
       EpiRow er;
       er.obase = 0; er.i0 = 0; er.rb_row = 0; er.e_mean = 0.f; er.e_rstd = 1.f;
-      if (row_ok) er = bd_epi_row(d, m);
+      if (row_ok) {                                // (b, i1, i0) are known from the tile: no divisions for the offset
+        er.i0 = i0;
+        er.obase = (long long)b * d.os_b + (long long)i1 * d.os_1 +
+                   (long long)(d.convt ? 4 * i0 - (d.convt == 1 ? 2 : 0) : i0) * d.os_0;
+        if (d.rowbias) er.rb_row = (int)((unsigned)m % (unsigned)d.rowbias_period);
+        if (d.e_stats) {
+          const int sl = bd_stat_slab(d, m);
+          er.e_mean = __ldg(d.e_stats + 2 * (size_t)sl);
+          er.e_rstd = __ldg(d.e_stats + 2 * (size_t)sl + 1);
+        }
+      }
       const int my_slab = (d.stats_out && row_ok) ? bd_stat_slab(d, m) : -1;
       float ssum = 0.f, ssq = 0.f;
       mbar_wait_relaxed(&tmem_full[a], (uint32_t)((tcount >> 1) & 1));
@@ -702,6 +852,19 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[a]);   // accumulator is free for tile i+2 while we finish tile i
+        if (fast >= 0) {
+          const uint32_t st_s = smem_u32(stage), ri_s = smem_u32(rinfo);
+          const int n0w = n0 + cbase;
+          constexpr int FRB = kPGroups >= 4 ? 2 : 4;
+          switch (fast) {
+            case 0: epi_fast_rows<BD_ACT_NONE, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 1: epi_fast_rows<BD_ACT_NONE, false, true, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 2: epi_fast_rows<BD_ACT_GELU, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 3: epi_fast_rows<BD_ACT_GLU, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            default: epi_fast_rows<BD_ACT_GLU, true, true, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+          }
+          __syncwarp();
+        } else {
         constexpr int CG = WC / 4 < 32 ? WC / 4 : 32;
         constexpr int RPI = 32 / CG;
         constexpr int RB = kPGroups >= 4 ? 2 : 4;
@@ -761,6 +924,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
           }
         }
         __syncwarp();   // staging rows are rewritten by the next tile
+        }
       } else {
         for (int c0 = 0; c0 < WC; c0 += CW) {
           if (n0 + cbase + c0 >= d.N) break;

@@ -291,7 +291,16 @@ class Engine:
                     nbytes=4.0 * M * hid, flops=4.0 * M * hid * C_, label="dconv_expand_stats",
                     detail=f"M={M} C={C_} hid={hid}")
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr2), slabs, float(T * 2 * C_), self._stream())
-            # (3) x += scale * GLU(gn(u)), in place
+            # (3) x += scale * GLU(gn(u)), in place.  Wide layers (hid >= 24, 2C >= 384) are a real GEMM: activate
+            #     h once, then the tensor-core arm contracts it with W2 and finishes GroupNorm / GLU / LayerScale /
+            #     residual in its epilogue.  Narrow layers stay on the dedicated CUDA-core kernel (K = 6 / 12).
+            if tc and hid >= 24:
+                self._k("bd_gn_gelu_apply", ptr(h), ptr(mr1), ptr(W[f"{p}.g1p"]), ptr(W[f"{p}.be1p"]), M, hp, T * Fr, Fr,
+                        self._stream(), nbytes=8.0 * M * hp, label="bd_gn_gelu_apply")
+                self._gemm(M=M, N=2 * C_, Cin=hp, x=h, w=W[f"{p}.w2p"], bias=W[f"{p}.b2"], e_stats=mr2,
+                           e_gamma=W[f"{p}.g2"], e_beta=W[f"{p}.be2"], act=_lib.ACT_GLU, resid=x, scale=W[f"{p}.scale"],
+                           out=x, stat=stat)
+                continue
             self._k("bd_dconv_expand_update", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
                     ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(mr2), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
                     ptr(W[f"{p}.scale"]), ptr(x), M, C_, T * Fr, Fr, self._stream(),
