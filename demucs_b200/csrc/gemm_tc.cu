@@ -514,7 +514,7 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   return v;
 }
 
-template <int ACT, bool E, bool RES, int WC, int RB>
+template <int ACT, bool E, bool RES, bool ROWB, bool CT, int WC, int RB>
 __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t stage_s, uint32_t rinfo_s, int lane, int n0w,
                                               float& ssum, float& ssq) {
   constexpr int LDT = WC + 4;
@@ -540,8 +540,20 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
       scl = ldg4(d.scale + no);
     }
   }
-  float* outp = d.out + no;
-  const float* resp = RES ? d.resid + no : nullptr;
+  // transposed conv: column n = (output phase rr, channel); the row offset already points at phase 0
+  int rr = 0;
+  long long colofs = no;
+  if (CT) {
+    const int cout = d.N >> 2;
+    rr = nc / cout;
+    colofs = (long long)rr * d.os_0 + (nc - rr * cout);
+    rr -= d.convt == 1 ? 2 : 0;
+  }
+  float* outp = d.out + colofs;
+  const float* resp = RES ? d.resid + colofs : nullptr;
+  const float* addp = CT && d.addend ? d.addend + colofs : nullptr;
+  const float* rbp = ROWB ? d.rowbias + no : nullptr;
+  const int rb_ld = ACT == BD_ACT_GLU ? d.N >> 1 : d.N;
   const uint32_t st_lane = stage_s + (uint32_t)(rsub * LDT + 4 * cg) * 4u;
   const uint32_t ri_lane = rinfo_s + (uint32_t)rsub * 32u;
 #pragma unroll 1
@@ -549,7 +561,7 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
     long long ob[RB];
     bool ok[RB];
     float mean[RB], rstd[RB];
-    float4 res[RB];
+    float4 res[RB];   // residual / row bias / skip operand (at most one of them per combination)
 #pragma unroll
     for (int u = 0; u < RB; ++u) {
       const uint32_t ra = ri_lane + (uint32_t)((it + u) * RPI) * 32u;
@@ -557,6 +569,17 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(ra));
       ob[u] = (long long)(((unsigned long long)w1 << 32) | w0);
       ok[u] = (int)w2 >= 0 && col_ok;
+      if (CT) ok[u] = ok[u] && (unsigned)(4 * (int)w2 + rr) < (unsigned)d.O0;
+      if (ROWB || CT) res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ROWB && ok[u]) {
+        if (ACT == BD_ACT_GLU) {
+          const float2 t = ldg2(rbp + (size_t)w3 * rb_ld);
+          res[u].x = t.x; res[u].y = t.y;
+        } else {
+          res[u] = ldg4(rbp + (size_t)w3 * rb_ld);
+        }
+      }
+      if (CT && addp && ok[u]) res[u] = ldg4(addp + ob[u]);
       if (E) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mean[u]), "=f"(rstd[u]) : "r"(ra + 16));
       if (RES) {
         res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -582,6 +605,10 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
       }
       if (ACT == BD_ACT_GLU) {
         float2 o2 = make_float2(v.x * sigmoid_fast(v.y), v.z * sigmoid_fast(v.w));
+        if (ROWB) {
+          o2.x += res[u].x;
+          o2.y += res[u].y;
+        }
         if (RES) {
           o2.x = fmaf(scl.x, o2.x, res[u].x);
           o2.y = fmaf(scl.y, o2.y, res[u].y);
@@ -599,6 +626,9 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
           v.x = fmaf(scl.x, v.x, res[u].x); v.y = fmaf(scl.y, v.y, res[u].y);
           v.z = fmaf(scl.z, v.z, res[u].z); v.w = fmaf(scl.w, v.w, res[u].w);
         }
+        if (ROWB || CT) {
+          v.x += res[u].x; v.y += res[u].y; v.z += res[u].z; v.w += res[u].w;
+        }
         if (ok[u]) {
           *reinterpret_cast<float4*>(outp + ob[u]) = v;
           ssum += (v.x + v.y) + (v.z + v.w);
@@ -611,8 +641,11 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
 
 // which compile-time combination (if any) covers this launch; uniform per kernel
 __device__ __forceinline__ int epi_fast_id(const bd_gemm_desc& d, bool vec, bool row_stats) {
-  if (!vec || row_stats || !d.out || d.convt || d.oc_split || d.rowbias || d.addend) return -1;
+  if (!vec || row_stats || !d.out || d.oc_split) return -1;
   const bool e = d.e_stats != nullptr, r = d.resid != nullptr;
+  if (d.convt) return (d.act == BD_ACT_GELU && !e && !r && !d.rowbias) ? 6 : -1;
+  if (d.addend) return -1;
+  if (d.rowbias) return (d.act == BD_ACT_GLU && !e && !r) ? 5 : -1;
   if (d.act == BD_ACT_NONE && !e) return r ? 1 : 0;
   if (d.act == BD_ACT_GELU && !e && !r) return 2;
   if (d.act == BD_ACT_GLU && !e && !r) return 3;
@@ -637,14 +670,18 @@ struct PCfg {
   static constexpr int kThreads = 32 * kEpiWarp0 + 128 * kPGroups;
   static constexpr int kTileBytesA = TBM * TBK * 4, kTileBytesB = TBN * TBK * 4;
   static constexpr int kStageBytesA = (X3 ? 2 : 1) * kTileBytesA, kStageBytesB = (X3 ? 2 : 1) * kTileBytesB;
-  static constexpr int kWarpCols = TBN / kPGroups;
+  // wide tiles: the epilogue groups split the COLUMNS of one tile (two accumulators, ping-pong); narrow tiles
+  // (TBN <= 32, the epilogue of one tile is too small to share): each group takes every kPGroups-th TILE
+  static constexpr bool kTileSplit = TBN <= 32;
+  static constexpr int kNAcc = kTileSplit ? kPGroups : 2;
+  static constexpr int kWarpCols = kTileSplit ? TBN : TBN / kPGroups;
   static constexpr int kStagingBytes = 4 * kPGroups * 32 * (kWarpCols + 4) * 4;
-  static constexpr int kTailBytes = 512 + 128 * kPGroups * 32;
+  static constexpr int kTailBytes = 512 + 128 * kPGroups * 32;   // barriers + TMEM slot, then the row tables
   static constexpr int kBudget = 227 * 1024 - 1024 - kTailBytes - kStagingBytes;
   static constexpr int kStagesRaw = kBudget / (kStageBytesA + kStageBytesB);
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > (kTileSplit ? 16 : 8) ? (kTileSplit ? 16 : 8) : kStagesRaw;
   static constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + kStagingBytes + 1024 + kTailBytes;
-  static constexpr int kTmemCols = 2 * TBN < 32 ? 32 : 2 * TBN;
+  static constexpr int kTmemCols = kNAcc * TBN < 32 ? 32 : kNAcc * TBN;
 };
 
 template <int TBK, int TBN, bool X3>
@@ -666,9 +703,11 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
   float* staging = reinterpret_cast<float*>(sB + kStages * kStageBytesB);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + C_::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;       // [2]
-  uint64_t* tmem_empty = tmem_full + 2;            // [2]
-  uint64_t* conv_bar = tmem_empty + 2;             // [kStages] X3: hi/lo tiles written by the splitter warps
+  constexpr int kNAcc = C_::kNAcc;
+  constexpr bool kTileSplit = C_::kTileSplit;
+  uint64_t* tmem_full = empty_bar + kStages;       // [kNAcc]
+  uint64_t* tmem_empty = tmem_full + kNAcc;        // [kNAcc]
+  uint64_t* conv_bar = tmem_empty + kNAcc;             // [kStages] X3: hi/lo tiles written by the splitter warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -680,9 +719,9 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
       mbar_init(&empty_bar[s], 1);
       mbar_init(&conv_bar[s], 128);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kNAcc; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4 * kPGroups);      // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], kTileSplit ? 4 : 4 * kPGroups);   // one arrival per epilogue warp of the tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -743,8 +782,8 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
       long long kbg = 0;
       int tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        const int a = tcount & 1;
-        mbar_wait_parked(&tmem_empty[a], (uint32_t)(((tcount >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
+        const int a = tcount % kNAcc;
+        mbar_wait_parked(&tmem_empty[a], (uint32_t)(((tcount / kNAcc) & 1) ^ 1));   // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(a * TBN);
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
@@ -799,7 +838,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
   } else if (warp >= C_::kEpiWarp0) {
     // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - first) / 4 =====
     const int quarter = warp & 3, ew = warp - C_::kEpiWarp0, grp = ew >> 2;
-    const int cbase = grp * WC;
+    const int cbase = kTileSplit ? 0 : grp * WC;
     const bool row_stats = d.stats_out && d.stat_mod != 1;
     const bool vec = bd_epi_vec_ok(d);
     const int fast = epi_fast_id(d, vec, row_stats);
@@ -808,9 +847,10 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
     RowInfo* rinfo = reinterpret_cast<RowInfo*>(((uintptr_t)(tmem_slot + 4) + 31) & ~(uintptr_t)31) + ew * 32;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      if (kTileSplit && tcount % kPGroups != grp) continue;
       int b, i0s, i1s, n0;
       decode(tile, b, i0s, i1s, n0);
-      const int a = tcount & 1;
+      const int a = tcount % kNAcc;
       const int r = quarter * 32 + lane;
       const int i0 = i0s + (r & (g.R0 - 1)), i1 = i1s + (r >> g.log2R0);
       const bool row_ok = i0 < d.I0 && i1 < d.I1;
@@ -830,7 +870,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
       }
       const int my_slab = (d.stats_out && row_ok) ? bd_stat_slab(d, m) : -1;
       float ssum = 0.f, ssq = 0.f;
-      mbar_wait_relaxed(&tmem_full[a], (uint32_t)((tcount >> 1) & 1));
+      mbar_wait_relaxed(&tmem_full[a], (uint32_t)((tcount / kNAcc) & 1));
       tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(a * TBN + cbase) + ((uint32_t)(quarter * 32) << 16);
       if (vec) {
@@ -857,11 +897,13 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
           const int n0w = n0 + cbase;
           constexpr int FRB = kPGroups >= 4 ? 2 : 4;
           switch (fast) {
-            case 0: epi_fast_rows<BD_ACT_NONE, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
-            case 1: epi_fast_rows<BD_ACT_NONE, false, true, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
-            case 2: epi_fast_rows<BD_ACT_GELU, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
-            case 3: epi_fast_rows<BD_ACT_GLU, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
-            default: epi_fast_rows<BD_ACT_GLU, true, true, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 0: epi_fast_rows<BD_ACT_NONE, false, false, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 1: epi_fast_rows<BD_ACT_NONE, false, true, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 2: epi_fast_rows<BD_ACT_GELU, false, false, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 3: epi_fast_rows<BD_ACT_GLU, false, false, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 4: epi_fast_rows<BD_ACT_GLU, true, true, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            case 5: epi_fast_rows<BD_ACT_GLU, false, false, true, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
+            default: epi_fast_rows<BD_ACT_GELU, false, false, false, true, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
           }
           __syncwarp();
         } else {
@@ -1124,17 +1166,21 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
   const cudaStream_t st = (cudaStream_t)stream;
   static const bool persist = getenv("BD_TC_NO_PERSIST") == nullptr;
-  if (persist && tbn >= 64) {   // compute-heavy tiles: persistent, overlapped epilogue
-    if (d.math == BD_MATH_TF32X3) {   // hi/lo stages are twice the size: 16-wide k-blocks keep 4 of them
+  if (persist) {   // persistent kernel, epilogue overlapped with the next tile's main loop
+#define BD_TC_PERSIST(TBK_, X3_)                                                                               \
+  (tbn == 16 ? launch_tc_persist<TBK_, 16, X3_>(d, g, items, st) : tbn == 32 ? launch_tc_persist<TBK_, 32, X3_>(d, g, items, st) \
+   : tbn == 64 ? launch_tc_persist<TBK_, 64, X3_>(d, g, items, st) : launch_tc_persist<TBK_, 128, X3_>(d, g, items, st))
+    if (d.math == BD_MATH_TF32X3) {   // hi/lo stages are twice the size: 16-wide k-blocks keep the ring deep
       g.cpb = d.Cin / 16;
-      rc = tbn == 64 ? launch_tc_persist<16, 64, true>(d, g, items, st) : launch_tc_persist<16, 128, true>(d, g, items, st);
+      rc = BD_TC_PERSIST(16, true);
     } else if (d.Cin % 32 == 0) {
       g.cpb = d.Cin / 32;
-      rc = tbn == 64 ? launch_tc_persist<32, 64, false>(d, g, items, st) : launch_tc_persist<32, 128, false>(d, g, items, st);
+      rc = BD_TC_PERSIST(32, false);
     } else {
       g.cpb = d.Cin / 16;
-      rc = tbn == 64 ? launch_tc_persist<16, 64, false>(d, g, items, st) : launch_tc_persist<16, 128, false>(d, g, items, st);
+      rc = BD_TC_PERSIST(16, false);
     }
+#undef BD_TC_PERSIST
     *handled = 1;
     return rc;
   }
