@@ -31,6 +31,7 @@ SEGMENTS_PER_GPU = 64
 SEG_LEN = 343980            # int(39/5 * 44100)
 STRIDE = 257985             # int(0.75 * SEG_LEN)
 SR = 44100
+STRICT_MODE = "tf32x3"
 METRIC = "htdemucs audio-seconds separated per second"
 UNIT = "audio-s/s"
 
@@ -100,7 +101,7 @@ def measured_peaks() -> dict:
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
-def cpu_apply_seconds(length: int, reps: int, threads: int):
+def cpu_apply_seconds(length: int, reps: int, threads: int, want_output: bool = False):
     """Time the reference algorithm's apply_model on the host CPU: the unmodified reference when
     its tree is present (build container), else the oracle port (GPU box)."""
     import torch
@@ -124,12 +125,14 @@ def cpu_apply_seconds(length: int, reps: int, threads: int):
 
         def run():
             return apply_model_oracle((W, cfg), mix, shifts=0, split=True, overlap=0.25)
-    times = []
+    times, out = [], None
     with torch.no_grad():
         for _ in range(reps):
             t0 = time.perf_counter()
-            run()
+            out = run()
             times.append(time.perf_counter() - t0)
+    if want_output:
+        return times, kind, (mix, out)
     return times, kind
 
 
@@ -178,6 +181,11 @@ def gpu_arm(args) -> None:
 
     model = D.htdemucs(mode=args.mode).to(dev)
     eng = model.engine()
+    # the error-compensated arithmetic (3xTF32: per-stem rel-L2 <= 1e-4, north_star's fp32/TF32 tolerance) is timed
+    # beside the headline mode (single-pass TF32: <= 1e-2, north_star's reduced-precision tolerance)
+    strict_model = None
+    if args.mode != STRICT_MODE and not args.no_strict:
+        strict_model = D.htdemucs(mode=STRICT_MODE).to(dev)
     nseg = SEGMENTS_PER_GPU * world
     length = nseg * STRIDE
     host_mix = synth_track(length).pin_memory()
@@ -191,6 +199,9 @@ def gpu_arm(args) -> None:
 
     def step_device():
         return D.apply_model(model, dev_mix, device=dev, **kw)
+
+    def step_strict():
+        return D.apply_model(strict_model, dev_mix, device=dev, **kw)
 
     host_out = torch.empty(1, 4, 2, length).pin_memory()
 
@@ -224,6 +235,13 @@ def gpu_arm(args) -> None:
     ms_e2e = timed(step_e2e, args.steps)
     track_s = length / SR
     value, e2e = track_s / (ms / 1e3), track_s / (ms_e2e / 1e3)
+    strict = None
+    if strict_model is not None:
+        for _ in range(2):
+            step_strict()
+        ms_strict = timed(step_strict, args.steps)
+        strict = {"mode": STRICT_MODE, "value": track_s / (ms_strict / 1e3), "unit": UNIT, "ms_per_step": ms_strict,
+                  "tolerance": "per-stem rel-L2 <= 1e-4"}
 
     # per-kernel device time + algorithmic work of ONE more step, with events around every launch
     prof = perf.profile_step(eng, step_device)
@@ -243,21 +261,32 @@ def gpu_arm(args) -> None:
                 "share_of_step": top["share"], "launches_per_step": top["count"],
                 "avg_launch_ms": top["ms"] / max(top["count"], 1),
                 "kernels": prof["table"]}
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        times, kind = cpu_apply_seconds(10 * SR, 3, threads)
+        times, kind, (cpu_mix, cpu_out) = cpu_apply_seconds(10 * SR, 3, threads, want_output=True)
         sec = sorted(times[1:])[len(times[1:]) // 2]
+        # the CPU run doubles as the checker: same weights, same clip, through the same public call
+        parity = {"against": kind, "clip": "10 s (2 segments), shifts=0, overlap=0.25", "per_stem_rel_l2_max": {},
+                  "tolerance": {"tf32": 1e-2, STRICT_MODE: 1e-4, "fp32": 1e-4}}
+        for name, mdl in ((args.mode, model), (STRICT_MODE, strict_model)):
+            if mdl is None:
+                continue
+            got = D.apply_model(mdl, cpu_mix.to(dev), shifts=0, split=True, overlap=0.25, device=dev).cpu()
+            err = max(float((got[0, s] - cpu_out[0, s]).norm() / cpu_out[0, s].norm()) for s in range(got.shape[1]))
+            parity["per_stem_rel_l2_max"][name] = err
         cpu_baseline = {"value": 10.0 / sec, "unit": UNIT, "cores": threads, "kind": kind,
                         "sample": "median of 2 x apply_model on a 10 s clip (2 segments) after 1 warm-up, "
                                   f"{threads} threads, torch {torch.__version__} CPU fp32"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if args.mode == "tf32" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"tf32": "tf32", "tf32x3": "tf32x3 (3-pass, fp32-accurate)"}.get(args.mode, "f32"),
+            "data": "synthetic",
             "config": workload_config(world, args.mode, args.batch),
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": host_mix.numel() * 4,
                     "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "strict": strict, "parity": parity,
             "model_roofline": {"segments_per_s": nseg / (ms / 1e3),
                                "tf32_roofline_segments_per_s_per_gpu": 1e3 / 0.742,
                                "frac": (nseg / world / (ms / 1e3)) / (1e3 / 0.742)}}
@@ -272,7 +301,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("BD_MODE", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--mode", default=os.environ.get("BD_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--no-strict", action="store_true", help="skip timing the error-compensated mode beside the headline")
     ap.add_argument("--batch", type=int, default=16, help="segments per forward")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
