@@ -203,11 +203,28 @@ def gpu_arm(args) -> None:
     def step_strict():
         return D.apply_model(strict_model, dev_mix, device=dev, **kw)
 
-    host_out = torch.empty(1, 4, 2, length).pin_memory()
+    # End-to-end step: host -> device copy of the input this rank consumes, apply_model, device -> host read of
+    # the sample range this rank produced (N = 1: the whole track both ways).  Over all ranks the reads cover the
+    # result exactly once; every rank still holds the complete result on its device after the gather.
+    if shard is None:
+        in_lo, in_hi, out_lo, out_hi = 0, length, 0, length
+    else:
+        lo_seg, hi_seg = shard.block(nseg)
+        first = max(0, lo_seg - shard.halo(SEG_LEN, STRIDE))
+        in_lo, in_hi = first * STRIDE, min(length, (hi_seg - 1) * STRIDE + SEG_LEN)
+        out_lo, out_hi = lo_seg * STRIDE, (length if hi_seg == nseg else hi_seg * STRIDE)
+    host_out = torch.empty(1, 4, 2, out_hi - out_lo).pin_memory()
+    e2e_mix = torch.zeros_like(dev_mix)
+    h2d_bytes = torch.tensor([2 * (in_hi - in_lo) * 4], dtype=torch.float64, device=dev)
+    d2h_bytes = torch.tensor([host_out.numel() * 4], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_bytes)
+        dist.all_reduce(d2h_bytes)
 
     def step_e2e():
-        out = D.apply_model(model, host_mix.to(dev, non_blocking=True), device=dev, **kw)
-        host_out.copy_(out, non_blocking=True)
+        e2e_mix[..., in_lo:in_hi].copy_(host_mix[..., in_lo:in_hi], non_blocking=True)
+        out = D.apply_model(model, e2e_mix, device=dev, **kw)
+        host_out.copy_(out[..., out_lo:out_hi], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(host_out[0, 0, 0, 0])
 
@@ -283,8 +300,8 @@ def gpu_arm(args) -> None:
             "vs_baseline": None, "dtype": {"tf32": "tf32", "tf32x3": "tf32x3 (3-pass, fp32-accurate)"}.get(args.mode, "f32"),
             "data": "synthetic",
             "config": workload_config(world, args.mode, args.batch),
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": host_mix.numel() * 4,
-                    "d2h_bytes_per_step": host_out.numel() * 4},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "strict": strict, "parity": parity,
             "model_roofline": {"segments_per_s": nseg / (ms / 1e3),
