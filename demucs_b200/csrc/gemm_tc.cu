@@ -870,6 +870,15 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
       }
       const int my_slab = (d.stats_out && row_ok) ? bd_stat_slab(d, m) : -1;
       float ssum = 0.f, ssq = 0.f;
+      if (d.resid && row_ok && !d.convt && !d.oc_split) {
+        // this lane's row of the residual operand (one 128-byte line for the warp's column range): start it on
+        // its way from HBM to L2 now, the epilogue reads it after the accumulator wait
+        const int c0 = n0 + cbase;
+        if (c0 < d.N) {
+          const float* pf = d.resid + er.obase + (d.act == BD_ACT_GLU ? c0 >> 1 : c0);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
+      }
       mbar_wait_relaxed(&tmem_full[a], (uint32_t)((tcount / kNAcc) & 1));
       tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(a * TBN + cbase) + ((uint32_t)(quarter * 32) << 16);
