@@ -91,6 +91,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(label: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) and tensor-pipe activity of the kernels
+    behind a profile label, from the committed ncu pass over one 16-segment forward
+    (profiles/r01_ncu_forward_b16_tf32.json, made by tools/ncu_forward_table.py).  None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_forward_b16_tf32.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)["kernels"]
+    if label.startswith("conv_gemm_tc<"):
+        tbn = label[len("conv_gemm_tc<"):-1]
+        rows = [r for r in table if r["kernel"].startswith("conv_gemm_tc_persist_kernel<") and
+                r["kernel"].split(",")[1].strip() == tbn and r["kernel"].rstrip(">").split(",")[2].strip() == "0"]
+    else:
+        key = {"attention_tc": "attention_tc_kernel<0>"}.get(label, label)
+        rows = [r for r in table if r["kernel"].startswith(key)]
+    if not rows:
+        return None
+    n = sum(r["launches"] for r in rows)
+    ms = sum(r["ms"] for r in rows)
+    return {"bytes_per_launch": sum(r["dram_mb"] for r in rows) * 1e6 / n, "launches": n,
+            "tensor_pipe_active": sum(r["tensor_pipe_active"] * r["ms"] for r in rows) / ms,
+            "source": "profiles/r01_ncu_forward_b16_tf32.json"}
+
+
 def measured_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -273,8 +298,11 @@ def gpu_arm(args) -> None:
         achieved, peak, unit = top["tflops"], tensor_peak, "TFLOP/s"
     else:
         achieved, peak, unit = top["gbs"], peaks["hbm_gbs"], "GB/s"
+    ncu = ncu_traffic(top["name"]) if args.mode == "tf32" else None
     roofline = {"kernel": top["name"], "bound": top["bound"], "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"],
+                "frac": achieved / peak, "traffic": ncu["bytes_per_launch"] if ncu else None,
+                "traffic_unit": "DRAM bytes per launch (ncu)", "ncu": ncu,
+                "algorithmic_bytes_per_launch": top.get("bytes_per_launch"), "peak_source": peaks["source"],
                 "share_of_step": top["share"], "launches_per_step": top["count"],
                 "avg_launch_ms": top["ms"] / max(top["count"], 1),
                 "kernels": prof["table"]}

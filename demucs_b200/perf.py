@@ -39,6 +39,7 @@ def profile_step(engine, fn: tp.Callable[[], tp.Any]) -> dict:
         table.append({"name": g["name"], "count": g["count"], "ms": round(g["ms"], 3),
                       "share": round(g["ms"] / total, 4), "tflops": round(g["flops"] / sec / 1e12, 3),
                       "gbs": round(g["bytes"] / sec / 1e9, 1),
+                      "bytes_per_launch": g["bytes"] / g["count"], "flops_per_launch": g["flops"] / g["count"],
                       "bound": "tensor" if intensity >= TF32_BALANCE else "hbm"})
     return {"table": table, "dominant": table[0], "total_ms": total, "launches": launches}
 

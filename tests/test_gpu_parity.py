@@ -287,3 +287,40 @@ def test_forward_htdemucs_tf32x3_mode(name):
     stems = stem_errors(got.cpu(), want)
     print("per-stem", stems)
     assert max(stems) < STEM_TOL
+
+
+def test_htdemucs_6s_shifts2_tf32x3():
+    """BASELINE config 3 in miniature: the 6-stem geometry (htdemucs_6s), overlap 0.25, shifts=2, two segments,
+    in the fp32-accurate tensor-core mode, against the oracle drawing the same shift offsets."""
+    from demucs_b200.config import htdemucs_6s_config
+    cfg = htdemucs_6s_config()
+    model = D.HTDemucs.from_config(cfg, init_seed=3, mode="tf32x3").to(DEV)
+    mix = synth_mix(1, 400000, 77)
+    random.seed(11)
+    out = D.apply_model(model, mix, shifts=2, split=True, overlap=0.25, device=DEV)
+    assert list(out.shape) == [1, 6, 2, 400000]
+    W = init_weights(cfg, 3)
+    random.seed(11)
+    with torch.no_grad():
+        want = apply_model_oracle((W, cfg), mix, shifts=2, split=True, overlap=0.25)
+    errs = stem_errors(out, want)
+    print("6s shifts=2 per-stem", errs)
+    assert max(errs) < STEM_TOL
+
+
+def test_bag_of_four_single_source_members_tf32():
+    """BASELINE config 4 in miniature (htdemucs_ft: four fine-tuned members, member i contributes source i only,
+    demucs/remote/htdemucs_ft.yaml) in the reduced-precision mode, against the oracle's weighted sum."""
+    cfg = htdemucs_config()
+    weights = [[1.0 if s == m else 0.0 for s in range(4)] for m in range(4)]
+    models = [D.HTDemucs.from_config(cfg, init_seed=10 + m, mode="tf32").to(DEV) for m in range(4)]
+    mix = synth_mix(1, 300000, 5)
+    out = D.apply_model(D.BagOfModels(models, weights), mix, shifts=0, split=True, overlap=0.25, device=DEV)
+    want = torch.zeros_like(out)
+    with torch.no_grad():
+        for m in range(4):
+            part = apply_model_oracle((init_weights(cfg, 10 + m), cfg), mix, shifts=0, split=True, overlap=0.25)
+            want[:, m] = part[:, m]
+    errs = stem_errors(out, want)
+    print("bag of 4 per-stem", errs)
+    assert max(errs) < FAST_TOL
