@@ -299,9 +299,12 @@ def gpu_arm(args) -> None:
     else:
         achieved, peak, unit = top["gbs"], peaks["hbm_gbs"], "GB/s"
     ncu = ncu_traffic(top["name"]) if args.mode == "tf32" else None
+    if ncu:   # the ncu pass ran 16-segment forwards; activations (all but the L2-resident weights) scale with the batch
+        ncu["captured_at_batch"] = 16
+        ncu["bytes_per_launch"] *= args.batch / 16
     roofline = {"kernel": top["name"], "bound": top["bound"], "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak, "traffic": ncu["bytes_per_launch"] if ncu else None,
-                "traffic_unit": "DRAM bytes per launch (ncu)", "ncu": ncu,
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "ncu": ncu,
                 "algorithmic_bytes_per_launch": top.get("bytes_per_launch"), "peak_source": peaks["source"],
                 "share_of_step": top["share"], "launches_per_step": top["count"],
                 "avg_launch_ms": top["ms"] / max(top["count"], 1),
@@ -348,7 +351,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("BD_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-strict", action="store_true", help="skip timing the error-compensated mode beside the headline")
-    ap.add_argument("--batch", type=int, default=16, help="segments per forward")
+    ap.add_argument("--batch", type=int, default=64, help="segments per forward (64 = one forward per step and GPU; ~36 GB)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
