@@ -230,10 +230,11 @@ def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor,
         n_begin = lo_seg * stride
         n_end = ps.length if hi_seg >= nseg else hi_seg * stride
         if n_local <= 0:
-            return
+            return nseg, stride, ps.length
     eng._k("bd_overlap_add", ptr(segs), ptr(weight), ptr(out), first, n_local, nseg, rows, valid, seg_len, stride,
            ps.length, out.shape[-1], ps.out_shift, n_begin, n_end, ptr(row_alpha), ps.alpha, int(accumulate),
            eng._stream(), nbytes=4.0 * rows * (n_local * min(seg_len, ps.length) + (n_end - n_begin) * (2 if accumulate else 1)))
+    return nseg, stride, ps.length
 
 
 def apply_model(model: tp.Union[BagOfModels, Model],
@@ -272,6 +273,7 @@ def apply_model(model: tp.Union[BagOfModels, Model],
     out = torch.zeros(batch * S * channels, length, device=device)
     totals = [0.] * S
     bar = None
+    plans: tp.Set[tp.Optional[tp.Tuple[int, int, int]]] = set()     # segment plans of the passes (None: shifted)
     for mi, sub in enumerate(models):
         original_device = next(iter(sub.parameters())).device
         sub.to(device)
@@ -309,15 +311,19 @@ def apply_model(model: tp.Union[BagOfModels, Model],
                 seg_s = float(sub.segment if segment is None else segment)
                 scale = float(format((1 - overlap) * seg_s, ".2f"))
                 bar = tqdm.tqdm(unit_scale=scale, ncols=120, unit='seconds')
-            run_pass(sub, src, ps, out, row_alpha, accumulate=(mi > 0 or si > 0 or shard is not None),
+            plan = run_pass(sub, src, ps, out, row_alpha, accumulate=(mi > 0 or si > 0 or shard is not None),
                      split=split, overlap=overlap,
                      transition_power=transition_power, segment=segment, batch_size=batch_size,
                      notify=notify if callback is not None else None, progress_bar=bar, shard=shard)
+            plans.add(plan if not shifts else None)
         sub.to(original_device)
     if bar is not None:
         bar.close()
     if shard is not None:
-        shard.combine(out)   # ranks hold disjoint sample ranges of every pass; sum them (NCCL all-reduce)
+        # ranks hold disjoint sample ranges of every pass: one all-gather when all passes share one unshifted
+        # segment plan, else an all-reduce of the zero-padded pieces
+        only = next(iter(plans)) if len(plans) == 1 else None
+        shard.combine(out, only)
     out = out.view(batch, S, channels, length)
     if bag_weights is not None:
         out /= torch.tensor(totals, dtype=torch.float32, device=device).view(1, S, 1, 1)

@@ -8,8 +8,8 @@ with the model weights replicated.  The only data-path exchange is what the over
 needs: rank r owns the output samples [lo_r*stride, hi_r*stride) and those also receive the
 tails of the ``halo`` segments just left of its block, which the left neighbour sends
 (point-to-point, ~11 MB per segment).  Afterwards every rank holds a disjoint range of the
-result; ``combine`` sums the zero-padded pieces with one all-reduce (in-switch NVLS reduction on
-NVSwitch systems).  The overlap-add kernel is given the block's global position, so the values
+result; ``combine`` exchanges the pieces with one all-gather (or, when the shift trick moves the
+owned ranges from pass to pass, sums the zero-padded pieces with one all-reduce).  The overlap-add kernel is given the block's global position, so the values
 are bit-identical to a single-GPU run.
 """
 from __future__ import annotations
@@ -73,6 +73,33 @@ class Shard:
     def _peer(self, rank_in_group: int) -> int:
         return rank_in_group if self.group is None else dist.get_global_rank(self.group, rank_in_group)
 
-    def combine(self, out: torch.Tensor) -> None:
-        if self.world > 1:
+    def combine(self, out: torch.Tensor, plan: tp.Optional[tp.Tuple[int, int, int]] = None) -> None:
+        """Assemble the stems on every rank.  ``out`` [rows, L] holds this rank's sample ranges and zeros elsewhere.
+
+        ``plan`` = (nseg, stride, length) when every pass used the same segment plan with no shift: rank q then
+        owns exactly the samples [lo_q*stride, hi_q*stride) (the last rank up to ``length``), so the pieces are
+        exchanged with ONE all-gather of compact [rows, max_len] buffers -- each rank receives (world-1)/world of
+        the result once, half the traffic of the general path.  Otherwise (shift trick: the owned ranges move
+        with the random offset of every pass) the zero-padded pieces are summed with an all-reduce.  Both give
+        the bit pattern of a single-GPU run."""
+        if self.world == 1:
+            return
+        if plan is None:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        nseg, stride, length = plan
+        ranges = []
+        for q in range(self.world):
+            lo, hi = self.block_of(q, nseg)
+            ranges.append((lo * stride, lo * stride) if hi == lo else
+                          (lo * stride, length if hi >= nseg else hi * stride))
+        width = max(b - a for a, b in ranges)
+        rows = out.shape[0]
+        a, b = ranges[self.rank]
+        local = torch.zeros(rows, width, dtype=out.dtype, device=out.device)
+        local[:, :b - a].copy_(out[:, a:b])
+        gathered = torch.empty(self.world * rows, width, dtype=out.dtype, device=out.device)   # rank-major
+        dist.all_gather_into_tensor(gathered, local, group=self.group)
+        for q, (a, b) in enumerate(ranges):
+            if q != self.rank and b > a:
+                out[:, a:b].copy_(gathered[q * rows:(q + 1) * rows, :b - a])

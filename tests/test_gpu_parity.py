@@ -324,3 +324,16 @@ def test_bag_of_four_single_source_members_tf32():
     errs = stem_errors(out, want)
     print("bag of 4 per-stem", errs)
     assert max(errs) < FAST_TOL
+
+
+def test_full_size_batch_64_items_are_independent():
+    """bench.py runs one 64-segment forward per step (11 M rows in the first layers): every item must come out as it
+    does alone (guards the 32-bit row arithmetic and the per-item statistics slabs at that size)."""
+    cfg = htdemucs_config()
+    eng = Engine(cfg, init_weights(cfg, 0, layer_scale=0.5), DEV, mode="tf32x3")
+    mix = synth_mix(64, cfg.segment_length, 21).to(DEV)
+    full = eng.forward(mix).clone()
+    assert torch.isfinite(full).all()
+    for b in (0, 37, 63):
+        one = eng.forward(mix[b:b + 1].contiguous())
+        assert rel_l2(one.cpu(), full[b:b + 1].cpu()) < 2e-6, b
