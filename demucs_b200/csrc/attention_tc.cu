@@ -98,12 +98,6 @@ __device__ __forceinline__ uint64_t desc_kmajor(const void* smem) {
   return (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-// MN-major SWIZZLE_128B operand: a 128-byte row holds 32 consecutive MN (= head-dim) elements of one K (= key)
-// index; 8 keys form the 1024-byte swizzle atom (SBO), the next 32 head-dim elements start LBO bytes further.
-__device__ __forceinline__ uint64_t desc_mnmajor(const void* smem, uint32_t lbo_bytes) {
-  return (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);

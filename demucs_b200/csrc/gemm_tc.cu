@@ -1,62 +1,50 @@
-// K3/K7 (tensor-core arm): tcgen05 / TMEM / TMA GEMM for sm_100a, TF32 inputs, fp32 accumulate.
+// K3/K4/K7 (tensor-core arm): persistent tcgen05 / TMEM / TMA implicit GEMM for sm_100a, TF32 inputs, fp32
+// accumulate.
 //
 //   out[m, n] = epilogue( sum_k A[m, k] * W[n, k] )      A: activations [M, K] row-major (K-major)
 //                                                        W: weights     [N, K] row-major (K-major)
-// Both operands are K-major, so one TMA box of 32 floats x 128 rows lands in shared memory as
-// 128-byte rows in the SWIZZLE_128B pattern that the UMMA shared-memory descriptor consumes
-// directly.  One CTA computes a 128x128 tile: a 128-lane x 128-column fp32 accumulator in TMEM,
-// fed by `tcgen05.mma.cta_group::1.kind::tf32` (M=128, N=128, K=8 per instruction).
+// Both operands are K-major, so one TMA box of 32 (16) floats x 128 rows lands in shared memory as 128-byte
+// (64-byte) rows in the SWIZZLE_128B (_64B) pattern that the UMMA shared-memory descriptor consumes directly.
+// `tcgen05.mma.cta_group::1.kind::tf32` (M=128, N=TBN, K=8 per instruction) accumulates a 128 x TBN fp32 tile
+// in tensor memory.
 //
-// Warp roles (192 threads):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> HBM;
-// warp w owns TMEM lanes 32*(w%4) .. +31).  Pipelines: smem full/empty mbarriers between TMA and
-// MMA (kStages deep), one tmem_full mbarrier between MMA and the epilogue.  Two CTAs fit per SM
-// (96 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps the other's main loop.
+// One CTA per SM walks the tiles (tile = blockIdx.x + i * gridDim.x, column block fastest so that the CTAs
+// running at the same time share the activation rows in L2):
+//   warp 0      TMA producer (one elected lane); the shared-memory ring (4..16 stages) never drains between tiles
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 4..7  (3xTF32 only) operand splitter: x -> rn_tf32(x), x - rn_tf32(x) in shared memory
+//   last 8..16  epilogue warps, warp w owns TMEM lanes 32*(w%4)..+31.  Wide tiles (TBN >= 64): the 2..4 warps of
+//               a lane quarter split the tile's columns and the accumulator is double-buffered, so the epilogue
+//               of tile i runs under the main loop of tile i+1.  Narrow tiles (TBN <= 32): each group of 4 warps
+//               takes every 4th tile, with 4 accumulators in flight.
+// The epilogue dumps its TMEM rows into a staging buffer, then walks them with lane = 4-column group so that
+// every global access is a contiguous run of the output row.
 //
-// Implicit GEMM: for a multi-tap convolution the K loop walks (tap, channel block); the A tile of a
-// tap is ONE rank-4 TMA box [channels x R0 positions x R1 rows x 1 item] of the channels-last
-// activation tensor shifted by the tap offset -- out-of-range coordinates are zero-filled by the TMA
-// unit, which is exactly the convolution's zero padding, so there is no im2col buffer and no
-// boundary code.  A 128-row tile is R1 x R0 output positions (R0 = 128 for long axes, 8..64 for
-// the short frequency axes of the inner layers).
+// Implicit GEMM: for a multi-tap convolution the K loop walks (tap, channel block); the A tile of a tap is ONE
+// rank-4 TMA box [channels x R0 positions x R1 rows x 1 item] of the channels-last activation tensor shifted by
+// the tap offset (rank 5 with the position split as 4q + r for the stride-4 encoder convolutions) --
+// out-of-range coordinates are zero-filled by the TMA unit, which is exactly the convolution's zero padding, so
+// there is no im2col buffer and no boundary code.  A 128-row tile is R1 x R0 output positions (R0 = 128 for
+// long axes, 8..64 for the short frequency axes of the inner layers).
 //
-// Covered layers (unit stride, no A-side transform, C_in % 16 == 0): every nn.Linear of the
-// cross-transformer (transformer.py:365,418,506-512), the channel up/down-samplers
-// (htdemucs.py:586-599), the encoder 1x1 rewrite + GLU (hdemucs.py:152-154), the decoder 3x3 / k=3
-// rewrite + GLU (hdemucs.py:312-313) and the transposed convolutions in their 3-tap form
-// (hdemucs.py:326-334).  The stride-4 encoder convolutions, the DConv branch (HBM-bound, N or K of
-// 6..48) and C_in <= 8 layers stay on the fp32 arm (gemm_simt.cu).
+// Covered layers (no A-side transform, C_in % 16 == 0): every nn.Linear of the cross-transformer
+// (transformer.py:365,418,506-512), the channel up/down-samplers (htdemucs.py:586-599), the encoder k=8/s=4
+// convolutions and 1x1 rewrite + GLU (hdemucs.py:110,152-154), the decoder 3x3 / k=3 rewrite + GLU
+// (hdemucs.py:312-313), the transposed convolutions in their 3-tap form (hdemucs.py:326-334), the DConv
+// dilated conv3 and, for hidden widths >= 24, its 1x1 expansion (demucs.py:138-153).  C_in <= 8 layers (first
+// encoder layer of each branch) stay on the fp32 arm (gemm_simt.cu).
 #include <cuda.h>
 #include <stdlib.h>
 #include "gemm_epilogue.cuh"
 
 namespace {
 
-#ifndef BD_TC_PIPE_BYTES
-#define BD_TC_PIPE_BYTES 98304
-#endif
 constexpr int TBM = 128;                           // tile rows (UMMA M)
-constexpr int kThreads = 192;
 
 // TBK floats per k-block: 32 -> 128B swizzle, 16 -> 64B swizzle.  TBN = tile columns = UMMA N (16..128):
 // narrow outputs (DConv hidden widths, last-layer channels) get narrow tiles instead of zero padding.
 // X3: error-compensated "3xTF32": every operand tile is split in shared memory into hi = rn_tf32(x) and
 // lo = x - hi and the product is accumulated as hi*hi + lo*hi + hi*lo (fp32-class accuracy, 3x the MMAs).
-template <int TBK, int TBN, bool X3>
-struct Cfg {
-  static constexpr int kTileBytesA = TBM * TBK * 4, kTileBytesB = TBN * TBK * 4;
-  static constexpr int kStageBytesA = kTileBytesA * (X3 ? 2 : 1), kStageBytesB = kTileBytesB * (X3 ? 2 : 1);
-  static constexpr int kStagesRaw = (X3 ? 196608 : BD_TC_PIPE_BYTES) / (kStageBytesA + kStageBytesB);   // 96 KB: 2 CTAs / SM
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kStagingBytes = 4 * 32 * (TBN + 4) * 4;
-  static constexpr int kTailBytes = 512 /*barriers*/ + 128 * 32 /*RowInfo*/;
-  static constexpr int smem_bytes(int stages) {
-    int pipe = stages * (kStageBytesA + kStageBytesB);
-    return (pipe > kStagingBytes ? pipe : kStagingBytes) + 1024 /*align slack*/ + kTailBytes;
-  }
-  static constexpr int kSmemBytes = smem_bytes(kStages);
-  static constexpr int kTmemCols = TBN < 32 ? 32 : TBN;
-};
 
 struct RowInfo {           // per-row epilogue constants, parked in shared memory (32 bytes)
   long long obase;
@@ -67,7 +55,6 @@ struct RowInfo {           // per-row epilogue constants, parked in shared memor
 };
 
 struct TileGeom {
-  int stages;            // smem pipeline depth actually used (<= Cfg::kStages; short K loops need fewer)
   int R0, R1;            // tile = R1 rows (i1) x R0 positions (i0), R0 * R1 == 128, powers of two
   int log2R0;
   int blocks0, blocks1;  // tiles along i0 / i1 per item
@@ -219,282 +206,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// ---- kernel -------------------------------------------------------------------------------------------
-template <int TBK, int TBN, bool X3>
-__global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                const __grid_constant__ CUtensorMap map_b,
-                                                                const bd_gemm_desc d, const TileGeom g) {
-  using C_ = Cfg<TBK, TBN, X3>;
-  constexpr int kStages = C_::kStages, kStageBytesA = C_::kStageBytesA, kStageBytesB = C_::kStageBytesB;
-  constexpr int kTileBytesA = C_::kTileBytesA, kTileBytesB = C_::kTileBytesB;
-  constexpr int kTmemCols = C_::kTmemCols;
-  constexpr int CW = TBN < 32 ? TBN : 32;            // columns per TMEM load
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int nstages = g.stages;
-  constexpr int kStagingBytes = 4 * 32 * (TBN + 4) * 4;   // epilogue staging, aliases the pipeline buffers
-  const int pipe_bytes = nstages * (kStageBytesA + kStageBytesB);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + nstages * kStageBytesA;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (pipe_bytes > kStagingBytes ? pipe_bytes : kStagingBytes));
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint64_t* conv_bar = tmem_full_bar + 1;            // [kStages] X3: hi/lo tiles written by the converter warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kStages);
-  __shared__ double red[8];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile -> (item b, row block, position block)
-  const int blk0 = blockIdx.x % g.blocks0;
-  const int tq = blockIdx.x / g.blocks0;
-  const int blk1 = tq % g.blocks1;
-  const int b = tq / g.blocks1;
-  const int i0s = blk0 * g.R0, i1s = blk1 * g.R1;
-  const int n0 = blockIdx.y * TBN;
-  const int nkb = d.taps * g.cpb;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-      mbar_init(&conv_bar[s], 128);
-    }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it at the end
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % nstages;
-        const uint32_t ph = (kb / nstages) & 1;
-        mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], kTileBytesA + kTileBytesB);
-        // A: the tap-shifted window of the activation tensor; out-of-range rows/positions read as zero
-        if (g.stride4) {   // output position i0 reads input 4*i0 + d0 = 4*(i0 + floor(d0/4)) + (d0 mod 4)
-          const int d0 = d.d0[tap];
-          tma_load_5d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, d0 & 3, i0s + (d0 >> 2), i1s + d.d1[tap], b);
-        } else {
-          tma_load_4d(&map_a, &full_bar[s], sA + s * kStageBytesA, cb * TBK, i0s + d.d0[tap], i1s + d.d1[tap], b);
-        }
-        tma_load_2d(&map_b, &full_bar[s], sB + s * kStageBytesB, tap * d.Cin + cb * TBK, n0);
-        if (++cb == g.cpb) {
-          cb = 0;
-          ++tap;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TBM, TBN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % nstages;
-        const uint32_t ph = (kb / nstages) & 1;
-        mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], ph);
-        tcgen05_fence_after();
-        const uint64_t adesc = make_kmajor_desc<TBK>(sA + s * kStageBytesA);
-        const uint64_t bdesc = make_kmajor_desc<TBK>(sB + s * kStageBytesB);
-#pragma unroll
-        for (int k = 0; k < TBK / 8; ++k) {   // UMMA_K = 8 tf32 = 32 B: advance the start address by 32 B >> 4
-          if constexpr (X3) {
-            const uint64_t alo = make_kmajor_desc<TBK>(sA + s * kStageBytesA + kTileBytesA);
-            const uint64_t blo = make_kmajor_desc<TBK>(sB + s * kStageBytesB + kTileBytesB);
-            umma_tf32(tmem_base, alo + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);   // small terms first
-            umma_tf32(tmem_base, adesc + 2 * k, blo + 2 * k, idesc, 1);
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
-          } else {
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
-        }
-        tcgen05_commit(&empty_bar[s]);      // frees the smem stage once these MMAs have read it
-      }
-      tcgen05_commit(tmem_full_bar);        // accumulator complete
-    }
-  } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    // TMEM rows come out one per lane; HBM wants a row's columns side by side.  Each warp dumps its 32 rows
-    // into the (now idle) pipeline shared memory, then walks them row by row with lane = 4-column group,
-    // so every global access of the fused epilogue is a contiguous run of the output row.
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const int i0 = i0s + (r & (g.R0 - 1)), i1 = i1s + (r >> g.log2R0);
-    const bool row_ok = i0 < d.I0 && i1 < d.I1;
-    const long long m = ((long long)b * d.I1 + i1) * d.I0 + i0;
-    if constexpr (X3) {
-      // ===== operand splitter: these 4 warps are idle during the main loop =====
-      const int et = threadIdx.x - 64;      // 0..127
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % nstages;
-        mbar_wait(&full_bar[s], (kb / nstages) & 1);
-        auto split = [&](uint8_t* base, int tile_bytes) {
-          float4* hi = reinterpret_cast<float4*>(base);
-          float4* lo = reinterpret_cast<float4*>(base + tile_bytes);
-          for (int i = et; i < tile_bytes / 16; i += 128) {
-            const float4 x = hi[i];
-            const float4 h = make_float4(rn_tf32(x.x), rn_tf32(x.y), rn_tf32(x.z), rn_tf32(x.w));
-            hi[i] = h;
-            lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-          }
-        };
-        split(sA + s * kStageBytesA, kTileBytesA);
-        split(sB + s * kStageBytesB, kTileBytesB);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> UMMA reads
-        mbar_arrive(&conv_bar[s]);
-      }
-    }
-    mbar_wait_relaxed(tmem_full_bar, 0);    // also: every MMA has finished reading the smem stages
-    tcgen05_fence_after();
-
-    EpiRow er;
-    er.obase = 0; er.i0 = 0; er.rb_row = 0; er.e_mean = 0.f; er.e_rstd = 1.f;
-    if (row_ok) er = bd_epi_row(d, m);
-    const bool row_stats = d.stats_out && d.stat_mod != 1;
-    const int my_slab = (row_stats && row_ok) ? bd_stat_slab(d, m) : -1;
-    float ssum = 0.f, ssq = 0.f;
-    const bool vec = bd_epi_vec_ok(d);
-    constexpr int LDT = TBN + 4;            // staging row pitch (floats): conflict-free float4 rows
-    float* stage = reinterpret_cast<float*>(smem) + (size_t)quarter * 32 * LDT;
-    RowInfo* rinfo = reinterpret_cast<RowInfo*>(((uintptr_t)(tmem_slot + 4) + 31) & ~(uintptr_t)31) + quarter * 32;
-    if (vec) {
-      rinfo[lane].obase = er.obase;
-      rinfo[lane].i0 = row_ok ? er.i0 : -1;
-      rinfo[lane].rb_row = er.rb_row;
-      rinfo[lane].e_mean = er.e_mean;
-      rinfo[lane].e_rstd = er.e_rstd;
-      for (int c0 = 0; c0 < TBN; c0 += CW) {
-        if (n0 + c0 >= d.N) break;          // warp-uniform
-        uint32_t v[CW];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-#pragma unroll
-        for (int j = 0; j < CW; j += 4)
-          *reinterpret_cast<float4*>(stage + lane * LDT + c0 + j) =
-              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                          __uint_as_float(v[j + 3]));
-      }
-      __syncwarp();
-      // lane -> (row within group, 4-column group): a warp instruction covers RPI rows x TBN columns
-      constexpr int CG = TBN / 4 < 32 ? TBN / 4 : 32;
-      constexpr int RPI = 32 / CG;
-      constexpr int RB = 4;                 // row groups whose memory operands are in flight together
-      const int cg = lane % CG, rsub = lane / CG;
-      const int n = n0 + 4 * cg;
-      const bool col_ok = n < d.N;
-      EpiCol ecol;
-      if (col_ok) ecol = bd_epi_cols4(d, n);
-      for (int it = 0; it < 32 / RPI; it += RB) {
-        EpiRow row[RB];
-        EpiMem mem[RB];
-        bool ok[RB];
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int rloc = (it + u) * RPI + rsub;
-          RowInfo ri;                        // explicit ld.shared (the compiler had demoted these to generic loads)
-          {
-            const uint32_t a = smem_u32(&rinfo[rloc]);
-            uint32_t w0, w1, w2, w3, w4, w5;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a));
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w4), "=r"(w5) : "r"(a + 16));
-            ri.obase = (long long)(((unsigned long long)w1 << 32) | w0);
-            ri.i0 = (int)w2;
-            ri.rb_row = (int)w3;
-            ri.e_mean = __uint_as_float(w4);
-            ri.e_rstd = __uint_as_float(w5);
-          }
-          row[u].obase = ri.obase; row[u].i0 = ri.i0; row[u].rb_row = ri.rb_row;
-          row[u].e_mean = ri.e_mean; row[u].e_rstd = ri.e_rstd;
-          ok[u] = (it + u) * RPI < 32 && ri.i0 >= 0 && col_ok;
-          if (ok[u]) mem[u] = bd_epi_fetch4(d, row[u], ecol);
-        }
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int rloc = (it + u) * RPI + rsub;
-          float rs = 0.f, rq = 0.f;
-          if (ok[u]) {
-            const float4 a = *reinterpret_cast<const float4*>(stage + rloc * LDT + 4 * cg);
-            bd_epi_finish4(d, row[u], ecol, a, mem[u], rs, rq);
-          }
-          if (row_stats) {                  // park the partial sums in the (consumed) staging row
-            __syncwarp();                   // every lane has read its accumulators of this row group
-            if ((it + u) * RPI < 32) *reinterpret_cast<float2*>(stage + rloc * LDT + 2 * cg) = make_float2(rs, rq);
-          } else {
-            ssum += rs;
-            ssq += rq;
-          }
-        }
-      }
-      if (row_stats) {                      // lane = row again: one pair of atomics per row, all rows in parallel
-        __syncwarp();
-        float rs = 0.f, rq = 0.f;
-#pragma unroll
-        for (int c = 0; c < CG; ++c) {
-          const float2 t = *reinterpret_cast<const float2*>(stage + lane * LDT + 2 * c);
-          rs += t.x;
-          rq += t.y;
-        }
-        if (my_slab >= 0) {
-          atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)rs);
-          atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)rq);
-        }
-      }
-    } else {
-      for (int c0 = 0; c0 < TBN; c0 += CW) {
-        if (n0 + c0 >= d.N) break;
-        uint32_t v[CW];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < d.N) {
-              float st;
-              if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) % CW]), st)) {
-                ssum += st;
-                ssq = fmaf(st, st, ssq);
-              }
-            }
-          }
-        }
-      }
-      if (row_stats && row_ok) {
-        atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)ssum);
-        atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)ssq);
-      }
-    }
-    if (d.stats_out && d.stat_mod == 1) {
-      double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
-      if (lane == 0) {
-        red[quarter] = ds;
-        red[4 + quarter] = dq;
-      }
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (d.stats_out && d.stat_mod == 1 && threadIdx.x == 0) {   // host guarantees one slab per tile
-    const int sl = bd_stat_slab(d, (long long)b * d.I1 * d.I0 + i0s);
-    atomicAdd(&d.stats_out[2 * (size_t)sl], red[0] + red[1] + red[2] + red[3]);
-    atomicAdd(&d.stats_out[2 * (size_t)sl + 1], red[4] + red[5] + red[6] + red[7]);
-  }
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
-  }
 }
 
 // ---- lean epilogue for the common layer shapes -----------------------------------------------------------
@@ -1056,48 +767,6 @@ int pow2_ceil(int v) {
 }
 
 template <int TBK, int TBN, bool X3>
-int launch_tc(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st) {
-  using C_ = Cfg<TBK, TBN, X3>;
-  alignas(64) CUtensorMap map_a, map_b;
-  // activations: (c, j0, j1, item); size-1 axes get a harmless contiguous stride
-  const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
-  cuuint64_t adim[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.J0, (cuuint64_t)d.J1, (cuuint64_t)items, 1};
-  cuuint64_t astr[4] = {(cuuint64_t)s0 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)sb * 4, 0};
-  cuuint32_t abox[5] = {(cuuint32_t)TBK, (cuuint32_t)g.R0, (cuuint32_t)g.R1, 1, 1};
-  int arank = 4;
-  if (g.stride4) {   // (c, r = pos % 4, q = pos / 4, j1, item)
-    arank = 5;
-    adim[1] = 4; adim[2] = (cuuint64_t)d.J0 / 4; adim[3] = (cuuint64_t)d.J1; adim[4] = (cuuint64_t)items;
-    astr[0] = (cuuint64_t)s0 * 4; astr[1] = (cuuint64_t)s0 * 16; astr[2] = (cuuint64_t)s1 * 4; astr[3] = (cuuint64_t)sb * 4;
-    abox[1] = 1; abox[2] = (cuuint32_t)g.R0; abox[3] = (cuuint32_t)g.R1; abox[4] = 1;
-  }
-  cuuint64_t bdim[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
-  cuuint64_t bstr[1] = {(cuuint64_t)d.K * 4};
-  cuuint32_t bbox[2] = {(cuuint32_t)TBK, (cuuint32_t)TBN};   // weight rows past N are zero-filled
-  if (!encode(&map_a, d.x, arank, adim, astr, abox, TBK) || !encode(&map_b, d.w, 2, bdim, bstr, bbox, TBK)) {
-    bd_set_error("bd_conv_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d Cin=%d J0=%d J1=%d)", d.M, d.N, d.K,
-                 d.Cin, d.J0, d.J1);
-    return BD_ERR_CUDA;
-  }
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<TBK, TBN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C_::kSmemBytes);
-    if (e != cudaSuccess) {
-      bd_set_error("bd_conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return BD_ERR_CUDA;
-    }
-    configured = true;
-  }
-  dim3 grid((unsigned)((long long)items * g.blocks1 * g.blocks0), (d.N + TBN - 1) / TBN);
-  TileGeom gg = g;
-  const int nkb = d.taps * g.cpb;
-  gg.stages = nkb < C_::kStages ? nkb : C_::kStages;
-  conv_gemm_tc_kernel<TBK, TBN, X3><<<grid, kThreads, C_::smem_bytes(gg.stages), st>>>(map_a, map_b, d, gg);
-  return bd_check_launch("conv_gemm_tc_kernel");
-}
-
-template <int TBK, int TBN, bool X3>
 int launch_tc_persist(const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st) {
   using C_ = PCfg<TBK, TBN, X3>;
   alignas(64) CUtensorMap map_a, map_b;
@@ -1174,38 +843,20 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   int rc;
   const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
   const cudaStream_t st = (cudaStream_t)stream;
-  static const bool persist = getenv("BD_TC_NO_PERSIST") == nullptr;
-  if (persist) {   // persistent kernel, epilogue overlapped with the next tile's main loop
 #define BD_TC_PERSIST(TBK_, X3_)                                                                               \
   (tbn == 16 ? launch_tc_persist<TBK_, 16, X3_>(d, g, items, st) : tbn == 32 ? launch_tc_persist<TBK_, 32, X3_>(d, g, items, st) \
    : tbn == 64 ? launch_tc_persist<TBK_, 64, X3_>(d, g, items, st) : launch_tc_persist<TBK_, 128, X3_>(d, g, items, st))
-    if (d.math == BD_MATH_TF32X3) {   // hi/lo stages are twice the size: 16-wide k-blocks keep the ring deep
-      g.cpb = d.Cin / 16;
-      rc = BD_TC_PERSIST(16, true);
-    } else if (d.Cin % 32 == 0) {
-      g.cpb = d.Cin / 32;
-      rc = BD_TC_PERSIST(32, false);
-    } else {
-      g.cpb = d.Cin / 16;
-      rc = BD_TC_PERSIST(16, false);
-    }
-#undef BD_TC_PERSIST
-    *handled = 1;
-    return rc;
-  }
-#define BD_TC_CASE(K_, N_) \
-  if (tbn == N_) rc = x3 ? launch_tc<K_, N_, true>(d, g, items, st) : launch_tc<K_, N_, false>(d, g, items, st); else
-  const bool x3 = d.math == BD_MATH_TF32X3;
-  if (d.Cin % 32 == 0) {
+  if (d.math == BD_MATH_TF32X3) {   // hi/lo stages are twice the size: 16-wide k-blocks keep the ring deep
+    g.cpb = d.Cin / 16;
+    rc = BD_TC_PERSIST(16, true);
+  } else if (d.Cin % 32 == 0) {
     g.cpb = d.Cin / 32;
-    BD_TC_CASE(32, 16) BD_TC_CASE(32, 32) BD_TC_CASE(32, 64)
-    rc = x3 ? launch_tc<32, 128, true>(d, g, items, st) : launch_tc<32, 128, false>(d, g, items, st);
+    rc = BD_TC_PERSIST(32, false);
   } else {
     g.cpb = d.Cin / 16;
-    BD_TC_CASE(16, 16) BD_TC_CASE(16, 32) BD_TC_CASE(16, 64)
-    rc = x3 ? launch_tc<16, 128, true>(d, g, items, st) : launch_tc<16, 128, false>(d, g, items, st);
+    rc = BD_TC_PERSIST(16, false);
   }
-#undef BD_TC_CASE
+#undef BD_TC_PERSIST
   *handled = 1;
   return rc;
 }
