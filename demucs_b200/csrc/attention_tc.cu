@@ -6,7 +6,8 @@
 // its softmax the tensor core runs the Q K^T / P V products of group 1 and vice versa, so neither side idles.
 //   S = Q K^T      : UMMA 128xTKx8 (tf32), Q and K tiles are K-major SWIZZLE_128B boxes straight from TMA
 //   P = softmax    : one query row per thread (TMEM lane = row: row max / sum need no shuffles), exp2 domain,
-//                    the row of S is read once into registers and P overwrites S IN PLACE in tensor memory;
+//                    two passes over the S row in tensor memory (maximum, then exponentials 32 columns at a time
+//                    with the next chunk's load in flight); P overwrites S IN PLACE in tensor memory;
 //                    the running maximum is only raised when it grows by more than 2^8 (lazy rescale), so the
 //                    O accumulator is rarely touched by the softmax warps
 //   O += P V       : UMMA 128x64x8 with the A operand read from TMEM (P never touches shared memory) and V^T
@@ -302,22 +303,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(
       const int kv_valid = min(TK, Tk - j * TK);
       mbar_wait(&s_full[g], (uint32_t)(i & 1));  // also: every earlier P V of this group has drained
       tc_fence_after();
-      uint32_t v[TK];
-#pragma unroll
-      for (int c0 = 0; c0 < TK; c0 += 32) tmem_ld32_nowait(s_addr + c0, v + c0);
-      tmem_ld_wait();
-      if (kv_valid < TK) {
-#pragma unroll
-        for (int c = 0; c < TK; ++c)
-          if (c >= kv_valid) v[c] = 0xff800000u;   // -inf: exp2 -> 0
-      }
+      // pass 1: row maximum (the S row is read again, chunk by chunk, in pass 2: tensor memory is cheap to read
+      // and 128 live values would not leave room for anything else)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < TK; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(v[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(v[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(v[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(v[c + 3]));
+      for (int h0 = 0; h0 < TK; h0 += 64) {
+        uint32_t w[64];
+        tmem_ld32_nowait(s_addr + h0, w);
+        tmem_ld32_nowait(s_addr + h0 + 32, w + 32);
+        tmem_ld_wait();
+        if (kv_valid < TK) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (h0 + c >= kv_valid) w[c] = 0xff800000u;
+        }
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(w[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(w[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(w[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(w[c + 3]));
+        }
       }
       const float m_cand = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
       const bool raise = m_cand > m_run + 8.0f;   // lazy: P stays below 2^8 with a stale maximum
@@ -336,30 +342,44 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(
         l_run *= corr;
         if (raise) m_run = m_cand;
       }
+      // pass 2: P = exp2(S * scale - m) over S in place, 32 columns at a time, the next chunk's load in flight
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      uint32_t va[32], vb[32];
+      tmem_ld32_nowait(s_addr, va);
+      tmem_ld_wait();
 #pragma unroll
       for (int c0 = 0; c0 < TK; c0 += 32) {
+        uint32_t* v = (c0 & 32) ? vb : va;
+        uint32_t* vn = (c0 & 32) ? va : vb;
+        if (c0 + 32 < TK) tmem_ld32_nowait(s_addr + c0 + 32, vn);
         uint32_t lo[X3 ? 32 : 1];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c0 + c]), sl2, -m_run));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c0 + c + 1]), sl2, -m_run));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(v[c0 + c + 2]), sl2, -m_run));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(v[c0 + c + 3]), sl2, -m_run));
+          const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_run), x1 = fmaf(__uint_as_float(v[c + 1]), sl2, -m_run);
+          const float x2 = fmaf(__uint_as_float(v[c + 2]), sl2, -m_run), x3 = fmaf(__uint_as_float(v[c + 3]), sl2, -m_run);
+          float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          float p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+          if (kv_valid < TK) {
+            if (c0 + c >= kv_valid) p0 = 0.f;
+            if (c0 + c + 1 >= kv_valid) p1 = 0.f;
+            if (c0 + c + 2 >= kv_valid) p2 = 0.f;
+            if (c0 + c + 3 >= kv_valid) p3 = 0.f;
+          }
           rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
           if (X3) {
             const float h0 = tf32_rna(p0), h1 = tf32_rna(p1), h2 = tf32_rna(p2), h3 = tf32_rna(p3);
-            v[c0 + c] = __float_as_uint(h0); v[c0 + c + 1] = __float_as_uint(h1);
-            v[c0 + c + 2] = __float_as_uint(h2); v[c0 + c + 3] = __float_as_uint(h3);
+            v[c] = __float_as_uint(h0); v[c + 1] = __float_as_uint(h1);
+            v[c + 2] = __float_as_uint(h2); v[c + 3] = __float_as_uint(h3);
             lo[c] = __float_as_uint(p0 - h0); lo[c + 1] = __float_as_uint(p1 - h1);
             lo[c + 2] = __float_as_uint(p2 - h2); lo[c + 3] = __float_as_uint(p3 - h3);
           } else {
-            v[c0 + c] = __float_as_uint(p0); v[c0 + c + 1] = __float_as_uint(p1);
-            v[c0 + c + 2] = __float_as_uint(p2); v[c0 + c + 3] = __float_as_uint(p3);
+            v[c] = __float_as_uint(p0); v[c + 1] = __float_as_uint(p1);
+            v[c + 2] = __float_as_uint(p2); v[c + 3] = __float_as_uint(p3);
           }
         }
-        tmem_st32(s_addr + c0, v + c0);          // P (hi) over S, in place
+        tmem_st32(s_addr + c0, v);               // P (hi) over S, in place
         if (X3) tmem_st32(tmem + lane_addr + col_plo(g) + c0, lo);
+        if (c0 + 32 < TK) tmem_ld_wait();
       }
       tmem_st_wait();
       l_run += (rs0 + rs1) + (rs2 + rs3);
