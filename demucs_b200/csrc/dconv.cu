@@ -201,14 +201,61 @@ int launch_expand(const float* h, int ldh, int hid, const float* mr1, const floa
 // A warp walks rows r = (c*K + k)*P + 32*sb + lane of one item, P = max(32, slabs_per_item): the slab of a lane
 // is the same in every iteration, lanes that share a slab (slabs_per_item < 32) are folded with shuffles, and
 // each slab's owner lane adds its BLK x BLK block of G (and sg) to the fp64 workspace.
+// The column sums of the quadratic forms depend on the weights only:
+//     sum_n w_n^T G w_n = sum_ab G[a][b] WW[a][b],   WW = W2^T W2;   sum_n b_n (w_n . sg) = wb . sg;   ...
+// wst = [WW (hid*hid) | ws = sum_n w_n (hid) | wb = sum_n b_n w_n (hid) | sum b_n | sum b_n^2], one warp per entry.
+__device__ __forceinline__ void dconv_wstats(const float* __restrict__ w2t, const float* __restrict__ b2, int hid, int N,
+                                             double* __restrict__ wst, int cta, int nctas) {
+  const int lane = threadIdx.x & 31;
+  const int E = hid * hid + 2 * hid + 2;
+  for (int e = cta * 8 + (threadIdx.x >> 5); e < E; e += nctas * 8) {
+    // operands of entry e: two rows of [w2t ; b2 ; 1]
+    const float* px = nullptr;
+    const float* py = nullptr;                                  // nullptr = the all-ones row
+    if (e < hid * hid) {
+      px = w2t + (size_t)(e / hid) * N;
+      py = w2t + (size_t)(e % hid) * N;
+    } else if (e < hid * hid + hid) {
+      px = w2t + (size_t)(e - hid * hid) * N;
+    } else if (e < hid * hid + 2 * hid) {
+      px = w2t + (size_t)(e - hid * hid - hid) * N;
+      py = b2;
+    } else {
+      px = b2;
+      py = e == hid * hid + 2 * hid ? nullptr : b2;
+    }
+    double acc = 0.0;
+    for (int n0 = 0; n0 < N; n0 += 256) {                       // 8 independent loads per lane in flight
+      float x[8], y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int n = n0 + 32 * u + lane;
+        x[u] = n < N ? __ldg(px + n) : 0.f;
+        y[u] = n < N ? (py ? __ldg(py + n) : 1.f) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fma((double)x[u], (double)y[u], acc);
+    }
+    acc = bd_warp_sum_d(acc);
+    if (lane == 0) wst[e] = acc;
+  }
+}
+
 template <int BLK>
 __global__ void __launch_bounds__(256, (BLK <= 8 ? 2 : 1)) dconv_gram_kernel(const float* __restrict__ h, int ldh, int hid,
                                                          const float* __restrict__ mr1, const float* __restrict__ g1,
                                                          const float* __restrict__ be1, double* __restrict__ gram,
-                                                         long long rpi, int spi, int items, int K, int ngroups) {
+                                                         long long rpi, int spi, int items, int K, int ngroups,
+                                                         int gram_ctas, const float* __restrict__ w2t,
+                                                         const float* __restrict__ b2, int N, double* __restrict__ wst) {
   constexpr int NACC = BLK * BLK + BLK, LDA = NACC | 1;       // odd pitch: lanes hit different banks
   __shared__ float buf[32 * LDA];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x >= gram_ctas) {
+    // the trailing CTAs compute the weight-only column sums while the others stream h (see dconv_wstats below)
+    dconv_wstats(w2t, b2, hid, N, wst, (int)blockIdx.x - gram_ctas, (int)gridDim.x - gram_ctas);
+    return;
+  }
   const int nblk = hid / BLK, nunits = nblk * (nblk + 1) / 2;
   const int P = spi > 32 ? spi : 32, nsb = P / 32;
   const int nown = spi < 32 ? spi : 32;                       // lanes that own a slab after the fold
@@ -216,7 +263,7 @@ __global__ void __launch_bounds__(256, (BLK <= 8 ? 2 : 1)) dconv_gram_kernel(con
   const int GS = hid * hid + hid;
   // CTA = 8 warps = 8 consecutive row chunks of one (item, block pair, slab block): their partial sums meet in
   // shared memory, so the fp64 workspace sees one atomic per value and CTA instead of one per warp
-  for (long long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+  for (long long wk = blockIdx.x; wk < nwork; wk += gram_ctas) {
     long long t = wk;
     const int c = (int)(t % ngroups) * 8 + warp; t /= ngroups;
     const int sb = (int)(t % nsb); t /= nsb;
@@ -334,84 +381,56 @@ __global__ void __launch_bounds__(256, (BLK <= 8 ? 2 : 1)) dconv_gram_kernel(con
   }
 }
 
-// The column sums of the quadratic forms depend on the weights only:
-//     sum_n w_n^T G w_n = sum_ab G[a][b] WW[a][b],   WW = W2^T W2;   sum_n b_n (w_n . sg) = wb . sg;   ...
-// wst = [WW (hid*hid) | ws = sum_n w_n (hid) | wb = sum_n b_n w_n (hid) | sum b_n | sum b_n^2], one warp per
-// entry.  The same launch clears the Gram workspace.
-__global__ void __launch_bounds__(256) dconv_wstats_kernel(const float* __restrict__ w2t, const float* __restrict__ b2, int hid,
-                                                           int N, double* __restrict__ wst, double* __restrict__ gram,
-                                                           long long gram_count) {
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < gram_count; i += (long long)gridDim.x * 256) gram[i] = 0.0;
-  const int lane = threadIdx.x & 31;
-  const int E = hid * hid + 2 * hid + 2;
-  for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < E; e += gridDim.x * 8) {
-    double acc = 0.0;
-    for (int n = lane; n < N; n += 32) {
-      double x, y;
-      if (e < hid * hid) {
-        x = (double)__ldg(w2t + (size_t)(e / hid) * N + n);
-        y = (double)__ldg(w2t + (size_t)(e % hid) * N + n);
-      } else if (e < hid * hid + hid) {
-        x = (double)__ldg(w2t + (size_t)(e - hid * hid) * N + n);
-        y = 1.0;
-      } else if (e < hid * hid + 2 * hid) {
-        x = (double)__ldg(w2t + (size_t)(e - hid * hid - hid) * N + n);
-        y = (double)__ldg(b2 + n);
-      } else {
-        x = (double)__ldg(b2 + n);
-        y = e == hid * hid + 2 * hid ? 1.0 : x;
-      }
-      acc = fma(x, y, acc);
-    }
-    acc = bd_warp_sum_d(acc);
-    if (lane == 0) wst[e] = acc;
-  }
-}
-
-// sums2[slab] += (sum u, sum u^2) from the slab's Gram matrix: one warp per slab
+// sums2[slab] += (sum u, sum u^2) from the slab's Gram matrix: one CTA per slab.  The Gram entries are cleared
+// after they are read, so the workspace is all zeros again when the call returns.
 template <int BLK>
-__global__ void __launch_bounds__(256) dconv_gram_eval_kernel(const double* __restrict__ gram, const double* __restrict__ wst,
-                                                              int hid, double* __restrict__ sums2, long long slabs, double R) {
-  const int lane = threadIdx.x & 31;
-  const long long slab = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (slab >= slabs) return;
+__global__ void __launch_bounds__(128) dconv_gram_eval_kernel(double* __restrict__ gram, const double* __restrict__ wst,
+                                                              int hid, double* __restrict__ sums2, double R) {
+  const long long slab = blockIdx.x;
   const int HH = hid * hid, GS = HH + hid;
-  const double* G = gram + slab * GS;
+  double* G = gram + slab * GS;
   double S = 0.0, Q = 0.0;
-  for (int i = lane; i < HH; i += 32) {
+  for (int i = threadIdx.x; i < HH; i += 128) {
     const int a = i / hid, b = i - a * hid;
     const double g = (a / BLK <= b / BLK) ? G[i] : G[b * hid + a];   // only blocks with bi <= bj were accumulated
     Q = fma(g, wst[i], Q);
   }
-  for (int a = lane; a < hid; a += 32) {
+  for (int a = threadIdx.x; a < hid; a += 128) {
     const double sg = G[HH + a];
     S = fma(wst[HH + a], sg, S);
     Q = fma(2.0 * wst[HH + hid + a], sg, Q);
   }
+  __shared__ double red[2][4];
   S = bd_warp_sum_d(S);
   Q = bd_warp_sum_d(Q);
-  if (lane == 0) {
-    sums2[2 * slab] += S + R * wst[HH + 2 * hid];
-    sums2[2 * slab + 1] += Q + R * wst[HH + 2 * hid + 1];
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = S;
+    red[1][threadIdx.x >> 5] = Q;
+  }
+  __syncthreads();                                             // every read of G is done
+  for (int i = threadIdx.x; i < GS; i += 128) G[i] = 0.0;
+  if (threadIdx.x == 0) {
+    sums2[2 * slab] += red[0][0] + red[0][1] + red[0][2] + red[0][3] + R * wst[HH + 2 * hid];
+    sums2[2 * slab + 1] += red[1][0] + red[1][1] + red[1][2] + red[1][3] + R * wst[HH + 2 * hid + 1];
   }
 }
 
 bool gram_supported(int hid, int ldh, long long rpi, int spi) {
   if (hid != 6 && hid != 12 && hid != 24 && hid != 48) return false;
-  if (ldh % (hid == 6 ? 2 : 4) != 0) return false;             // vector loads of the h rows
+  if (ldh % 2 != 0) return false;                              // float2 loads of the h rows
   if (spi <= 0 || rpi % spi != 0) return false;
   return spi >= 32 ? spi % 32 == 0 : 32 % spi == 0;
 }
 
-template <int HID, int BLK>
+constexpr int GRAM_BLK = 6;
+
 int launch_gram(const float* h, int ldh, int hid, const float* mr1, const float* g1, const float* be1, const float* w2t,
                 const float* b2, double* sums2, double* gram, long long M, int C, long long rpi, int spi, cudaStream_t st) {
+  constexpr int BLK = GRAM_BLK;
   const int items = (int)(M / rpi);
   const long long slabs = (long long)items * spi;
   const int GS = hid * hid + hid;
   double* wst = gram + slabs * GS;                            // weight-only sums live behind the Gram matrices
-  dconv_wstats_kernel<<<148, 256, 0, st>>>(w2t, b2, hid, 2 * C, wst, gram, slabs * GS);
-  if (bd_check_launch("dconv_wstats_kernel") != BD_OK) return BD_ERR_CUDA;
   const int P = spi > 32 ? spi : 32, nsb = P / 32, nblk = hid / BLK, nunits = nblk * (nblk + 1) / 2;
   const long long periods = (rpi + P - 1) / P;               // iterations needed to cover an item
   // enough CTAs (8 warps each) to fill the machine, at least 8 rows per lane to amortise the reduction
@@ -423,9 +442,11 @@ int launch_gram(const float* h, int ldh, int hid, const float* mr1, const float*
   ngroups = (periods + 8LL * K - 1) / (8LL * K);
   long long grid = base * ngroups;
   if (grid > 148LL * 8) grid = 148LL * 8;
-  dconv_gram_kernel<BLK><<<(unsigned)grid, 256, 0, st>>>(h, ldh, hid, mr1, g1, be1, gram, rpi, spi, items, K, (int)ngroups);
+  const int wst_ctas = 148;
+  dconv_gram_kernel<BLK><<<(unsigned)grid + wst_ctas, 256, 0, st>>>(h, ldh, hid, mr1, g1, be1, gram, rpi, spi, items, K,
+                                                                    (int)ngroups, (int)grid, w2t, b2, 2 * C, wst);
   if (bd_check_launch("dconv_gram_kernel") != BD_OK) return BD_ERR_CUDA;
-  dconv_gram_eval_kernel<BLK><<<(unsigned)((slabs + 7) / 8), 256, 0, st>>>(gram, wst, hid, sums2, slabs, (double)(rpi / spi));
+  dconv_gram_eval_kernel<BLK><<<(unsigned)slabs, 128, 0, st>>>(gram, wst, hid, sums2, (double)(rpi / spi));
   return bd_check_launch("dconv_gram_eval_kernel");
 }
 
@@ -438,12 +459,8 @@ int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rs
                           long long M, int C, long long rows_per_item, int slabs_per_item, void* stream) {
   BD_REQUIRE(hid > 0 && hid <= MAX_HID && C % 2 == 0 && ldh >= hid && M > 0, "bd_dconv_expand_stats: bad sizes (hid=%d C=%d)", hid, C);
   if (gram_ws && M % rows_per_item == 0 && gram_supported(hid, ldh, rows_per_item, slabs_per_item)) {
-#define BD_GRAM_ARGS h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, sums2, gram_ws, M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream
-    if (hid == 6) return launch_gram<6, 6>(BD_GRAM_ARGS);
-    if (hid == 12) return launch_gram<12, 12>(BD_GRAM_ARGS);
-    if (hid == 24) return launch_gram<24, 12>(BD_GRAM_ARGS);
-    return launch_gram<48, 12>(BD_GRAM_ARGS);
-#undef BD_GRAM_ARGS
+    return launch_gram(h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, sums2, gram_ws, M, C, rows_per_item,
+                       slabs_per_item, (cudaStream_t)stream);
   }
   return launch_expand<false>(h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, sums2, nullptr, nullptr, nullptr, nullptr,
                               nullptr, M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream);

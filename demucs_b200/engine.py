@@ -285,7 +285,8 @@ class Engine:
             # (2) statistics of u = conv1x1(gelu(gn(h))) WITHOUT storing u: the expanded [.., 2C] tensor never
             #     touches HBM, both passes recompute it from the 8x narrower h (csrc/dconv.cu)
             sums.zero_()
-            gram = self._buf(key, "dconv_gram", (slabs + 1) * (hid * hid + hid) + hid + 2, dtype=torch.float64)
+            gram = self._buf(key, f"dconv_gram{tag}.{hid}", (slabs + 1) * (hid * hid + hid) + hid + 2, dtype=torch.float64,
+                             zero=True)     # zero once: the kernels hand it back cleared
             self._k("bd_dconv_expand_stats", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
                     ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(sums), ptr(gram), M, C_, T * Fr, Fr, self._stream(),
                     nbytes=4.0 * M * hid, flops=4.0 * M * hid * C_, label="dconv_expand_stats",

@@ -126,8 +126,9 @@ int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float*
  *   h [M, ldh] holds the conv3 output (first `hid` columns), w2t [hid, 2C] is the transposed 1x1 weight with
  *   interleaved (value, gate) columns, b2/gamma2/beta2 [2C] interleaved likewise.
  * _stats : sums2[slab] += (sum, sumsq) of u = W2 gelu(gn1(h)) + b2            (u is never stored)
- *          gram_ws: optional workspace of (slabs + 1) * (hid*hid + hid) + hid + 2 doubles.  When given (hid in 6/12/24/48) the
- *          sums are derived from the slab's Gram matrix sum(g g^T): hid^2 instead of hid*2C products per row.
+ *          gram_ws: optional workspace of (slabs + 1) * (hid*hid + hid) + hid + 2 doubles, ALL ZERO on entry (it is
+ *          returned all zero in its first slabs*(hid*hid+hid) entries).  When given (hid in 6/12/24/48) the sums are
+ *          derived from the slab's Gram matrix sum(g g^T): hid^2 instead of hid*2C products per row.
  * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place) */
 int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
                           const float* beta1, const float* w2t, const float* b2, double* sums2, double* gram_ws,
