@@ -62,7 +62,7 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_finalize_group_stats": [_P, _P, _I, _D, _P],
     "bd_dconv_tail": [_P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "bd_dconv_expand_stats": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
-    "bd_dconv_expand_update": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
+    "bd_dconv_expand_update": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _I, _P],
     "bd_gn_gelu_apply": [_P, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "bd_layer_norm": [_P, _P, _P, _P, _P, _I, _LL, _I, _P],
     "bd_item_stats": [_P, _P, _I, _LL, _P],

@@ -450,6 +450,163 @@ int launch_gram(const float* h, int ldh, int hid, const float* mr1, const float*
   return bd_check_launch("dconv_gram_eval_kernel");
 }
 
+
+// ---- pass 2 on the warp-level tensor cores (single-pass TF32 mode) ------------------------------------------------
+// The 1x1 expansion is a [rows x (hid+1)] x [(hid+1) x 2C] product with hid = 6..48: one to seven UMMA_K steps,
+// so on a tcgen05 tile the epilogue is the whole kernel.  mma.sync.m16n8k8.tf32 works on registers instead: the
+// bias is folded in as row `hid` against a constant 1 in g, GroupNorm + GELU of h happen while the A fragments
+// are built, a warp takes 32 rows (two 16-row fragments), and the accumulator fragment hands every thread adjacent
+// (value, gate) column pairs of two rows -- a GLU pair -- so GroupNorm, GLU, LayerScale and the residual update
+// happen in place on the fragment, and the results go through a per-warp staging tile so that x is updated with
+// contiguous float4 runs.  ~2.4x fewer instructions per row than the FFMA kernel above, which stays in charge
+// of the fp32 and 3xTF32 modes (it is exact, and faster than three MMA passes).
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// CTA = 8 warps that share one block of 96 interleaved columns (48 channels) of the expansion: its weights sit in
+// shared memory as tf32 [96][8*KS + 4] (the pitch makes the B-fragment loads conflict-free), every warp walks
+// 32-row tiles.  KS = k-steps of 8: hid 6 -> 1, 12 -> 2, 24 -> 4, 48 -> 7 (row `hid` carries the bias).
+template <int HID>
+__global__ void __launch_bounds__(256) dconv_update_mma_kernel(
+    const float* __restrict__ h, int ldh, const float* __restrict__ mr1, const float* __restrict__ g1,
+    const float* __restrict__ be1, const float* __restrict__ w2t /*[hid][2C]*/, const float* __restrict__ b2,
+    const float* __restrict__ mr2, const float* __restrict__ g2, const float* __restrict__ be2,
+    const float* __restrict__ scale, float* __restrict__ x, long long M, int C, long long rows_per_item,
+    int slabs_per_item) {
+  constexpr int KS = (HID + 1 + 7) / 8, KP = 8 * KS + 4;
+  constexpr int NB = 96, CB = 48, NT = NB / 8;     // columns / channels / column fragments per block
+  constexpr int LDT = CB + 4;                      // staging pitch: the fragment scatter hits 32 different banks
+  const int N = 2 * C;
+  const int n_lo = blockIdx.y * NB, c_lo = blockIdx.y * CB;
+  extern __shared__ __align__(16) float sm[];
+  uint32_t* sW = reinterpret_cast<uint32_t*>(sm);  // [NB][KP] tf32
+  float* sG = sm + NB * KP;                        // [NB]
+  float* sBe = sG + NB;                            // [NB]
+  float* sS = sBe + NB;                            // [CB]
+  float* sT = sS + CB + (threadIdx.x >> 5) * (32 * LDT);   // [32 rows][LDT] per warp
+  for (int i = threadIdx.x; i < NB * 8 * KS; i += 256) {
+    const int n = i / (8 * KS), k = i - n * (8 * KS);
+    const float w = k < HID ? __ldg(w2t + (size_t)k * N + n_lo + n) : (k == HID ? __ldg(b2 + n_lo + n) : 0.f);
+    sW[n * KP + k] = to_tf32(w);
+  }
+  for (int i = threadIdx.x; i < NB; i += 256) {
+    sG[i] = __ldg(g2 + n_lo + i);
+    sBe[i] = __ldg(be2 + n_lo + i);
+  }
+  for (int i = threadIdx.x; i < CB; i += 256) sS[i] = __ldg(scale + c_lo + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  float ga[2 * KS], bea[2 * KS];                   // GroupNorm affine of this thread's k indices: 8*ks + tig (+4)
+#pragma unroll
+  for (int j = 0; j < 2 * KS; ++j) {
+    const int k = 8 * (j >> 1) + tig + 4 * (j & 1);
+    ga[j] = k < HID ? __ldg(g1 + k) : 0.f;
+    bea[j] = k < HID ? __ldg(be1 + k) : 0.f;
+  }
+  const long long ntiles = (M + 31) / 32;
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
+    const long long m0 = tile * 32;
+    // this thread's 4 rows: gid, gid + 8 (fragment 0), gid + 16, gid + 24 (fragment 1)
+    uint32_t ah[2][KS][4];
+    float m2[4], r2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long m = m0 + gid + 8 * q;
+      const long long mm = m < M ? m : m0;
+      const long long slab = (mm / rows_per_item) * slabs_per_item + (mm % slabs_per_item);
+      const float mean1 = __ldg(mr1 + 2 * slab), rstd1 = __ldg(mr1 + 2 * slab + 1);
+      m2[q] = __ldg(mr2 + 2 * slab);
+      r2[q] = __ldg(mr2 + 2 * slab + 1);
+      const float* hr = h + mm * ldh;
+      const int f = q >> 1, hi8 = q & 1;
+      // fragment element order: a0 (row gid, k tig), a1 (row gid+8, k tig), a2 (row gid, k tig+4), a3 (row gid+8, k tig+4)
+#pragma unroll
+      for (int j = 0; j < 2 * KS; ++j) {
+        const int k = 8 * (j >> 1) + tig + 4 * (j & 1);
+        float v = k == HID ? 1.f : 0.f;
+        if (k < HID) v = bd_gelu(fmaf((__ldg(hr + k) - mean1) * rstd1, ga[j], bea[j]));
+        ah[f][j >> 1][2 * (j & 1) + hi8] = to_tf32(v);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int n = 8 * nt + 2 * tig;                              // (value, gate) columns of this thread
+      const float2 gam = *reinterpret_cast<const float2*>(sG + n), bet = *reinterpret_cast<const float2*>(sBe + n);
+      const int ch = n >> 1;
+      const float sc = sS[ch];
+      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t b0 = sW[(8 * nt + gid) * KP + 8 * ks + tig], b1 = sW[(8 * nt + gid) * KP + 8 * ks + tig + 4];
+        mma_tf32_16x8x8(c[0], ah[0][ks], b0, b1);
+        mma_tf32_16x8x8(c[1], ah[1][ks], b0, b1);
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+#pragma unroll
+        for (int hi8 = 0; hi8 < 2; ++hi8) {
+          const int q = 2 * f + hi8;
+          const float val = fmaf((c[f][2 * hi8] - m2[q]) * r2[q], gam.x, bet.x);
+          const float gate = fmaf((c[f][2 * hi8 + 1] - m2[q]) * r2[q], gam.y, bet.y);
+          sT[(gid + 8 * q) * LDT + ch] = sc * val * bd_sigmoid(gate);
+        }
+      }
+    }
+    // the block's 48 channels of a row are one contiguous 192-byte run of x: float4 accesses, lane = consecutive float4
+    __syncwarp();
+    const long long left = M - m0;
+    const int nrows = left < 32 ? (int)left : 32;
+#pragma unroll
+    for (int j0 = 0; j0 < CB / 4; j0 += 4) {       // 12 float4 per lane, 4 loads in flight
+      float4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = lane + 32 * (j0 + u), row = i / (CB / 4), c4 = i - row * (CB / 4);
+        if (row < nrows) xv[u] = *reinterpret_cast<const float4*>(x + (m0 + row) * C + c_lo + 4 * c4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = lane + 32 * (j0 + u), row = i / (CB / 4), c4 = i - row * (CB / 4);
+        if (row < nrows) {
+          const float4 d = *reinterpret_cast<const float4*>(sT + row * LDT + 4 * c4);
+          *reinterpret_cast<float4*>(x + (m0 + row) * C + c_lo + 4 * c4) =
+              make_float4(xv[u].x + d.x, xv[u].y + d.y, xv[u].z + d.z, xv[u].w + d.w);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int HID>
+int launch_update_mma(const float* h, int ldh, const float* mr1, const float* g1, const float* be1, const float* w2t,
+                      const float* b2, const float* mr2, const float* g2, const float* be2, const float* scale, float* x,
+                      long long M, int C, long long rpi, int spi, cudaStream_t st) {
+  constexpr int KS = (HID + 1 + 7) / 8, KP = 8 * KS + 4;
+  const int nblk = C / 48;
+  long long gx = ((M + 31) / 32 + 7) / 8;
+  const long long cap = (148LL * 4 + nblk - 1) / nblk;          // ~4 CTAs per SM over all column blocks
+  if (gx > cap) gx = cap;
+  const int smem = (96 * KP + 2 * 96 + 48 + 8 * 32 * 52) * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(dconv_update_mma_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    bd_set_error("bd_dconv_expand_update: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return BD_ERR_CUDA;
+  }
+  dconv_update_mma_kernel<HID><<<dim3((unsigned)gx, nblk), 256, smem, st>>>(h, ldh, mr1, g1, be1, w2t, b2, mr2, g2, be2,
+                                                                           scale, x, M, C, rpi, spi);
+  return bd_check_launch("dconv_update_mma_kernel");
+}
+
 }  // namespace
 
 extern "C" {
@@ -469,8 +626,16 @@ int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rs
 int bd_dconv_expand_update(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
                            const float* beta1, const float* w2t, const float* b2, const float* mean_rstd2,
                            const float* gamma2, const float* beta2, const float* scale, float* x, long long M, int C,
-                           long long rows_per_item, int slabs_per_item, void* stream) {
+                           long long rows_per_item, int slabs_per_item, int math, void* stream) {
   BD_REQUIRE(hid > 0 && hid <= MAX_HID && C % 2 == 0 && ldh >= hid && M > 0, "bd_dconv_expand_update: bad sizes (hid=%d C=%d)", hid, C);
+  if (math == BD_MATH_TF32 && C % 48 == 0 && (hid == 6 || hid == 12 || hid == 24 || hid == 48)) {
+#define BD_MMA_ARGS h, ldh, mean_rstd1, gamma1, beta1, w2t, b2, mean_rstd2, gamma2, beta2, scale, x, M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream
+    if (hid == 6) return launch_update_mma<6>(BD_MMA_ARGS);
+    if (hid == 12) return launch_update_mma<12>(BD_MMA_ARGS);
+    if (hid == 24) return launch_update_mma<24>(BD_MMA_ARGS);
+    return launch_update_mma<48>(BD_MMA_ARGS);
+#undef BD_MMA_ARGS
+  }
   return launch_expand<true>(h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, nullptr, mean_rstd2, gamma2, beta2, scale, x,
                              M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream);
 }

@@ -292,10 +292,11 @@ class Engine:
                     nbytes=4.0 * M * hid, flops=4.0 * M * hid * C_, label="dconv_expand_stats",
                     detail=f"M={M} C={C_} hid={hid}")
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr2), slabs, float(T * 2 * C_), self._stream())
-            # (3) x += scale * GLU(gn(u)), in place.  Wide layers (hid >= 24, 2C >= 384) are a real GEMM: activate
-            #     h once, then the tensor-core arm contracts it with W2 and finishes GroupNorm / GLU / LayerScale /
-            #     residual in its epilogue.  Narrow layers stay on the dedicated CUDA-core kernel (K = 6 / 12).
-            if tc and hid >= 24:
+            # (3) x += scale * GLU(gn(u)), in place: the dedicated kernels of csrc/dconv.cu (mma.sync fragments in
+            #     "tf32" mode, exact FFMA otherwise).  The widest layers (hid 48; in "tf32x3" also hid 24) are a real
+            #     GEMM and go through the tcgen05 kernel instead: activate h once, then GroupNorm / GLU /
+            #     LayerScale / residual in the GEMM epilogue.
+            if tc and hid >= (48 if self.mode == "tf32" else 24):
                 self._k("bd_gn_gelu_apply", ptr(h), ptr(mr1), ptr(W[f"{p}.g1p"]), ptr(W[f"{p}.be1p"]), M, hp, T * Fr, Fr,
                         self._stream(), nbytes=8.0 * M * hp, label="bd_gn_gelu_apply")
                 self._gemm(M=M, N=2 * C_, Cin=hp, x=h, w=W[f"{p}.w2p"], bias=W[f"{p}.b2"], e_stats=mr2,
@@ -304,7 +305,7 @@ class Engine:
                 continue
             self._k("bd_dconv_expand_update", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
                     ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(mr2), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
-                    ptr(W[f"{p}.scale"]), ptr(x), M, C_, T * Fr, Fr, self._stream(),
+                    ptr(W[f"{p}.scale"]), ptr(x), M, C_, T * Fr, Fr, self._math(), self._stream(),
                     nbytes=4.0 * M * (hid + 2 * C_), flops=4.0 * M * hid * C_, label="dconv_expand_update",
                     detail=f"M={M} C={C_} hid={hid}")
 

@@ -129,14 +129,15 @@ int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float*
  *          gram_ws: optional workspace of (slabs + 1) * (hid*hid + hid) + hid + 2 doubles, ALL ZERO on entry (it is
  *          returned all zero in its first slabs*(hid*hid+hid) entries).  When given (hid in 6/12/24/48) the sums are
  *          derived from the slab's Gram matrix sum(g g^T): hid^2 instead of hid*2C products per row.
- * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place) */
+ * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place); math = BD_MATH_*: the
+ *          BD_MATH_TF32 runs the expansion on mma.sync tf32 fragments, the other modes in exact fp32 */
 int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
                           const float* beta1, const float* w2t, const float* b2, double* sums2, double* gram_ws,
                           long long M, int C, long long rows_per_item, int slabs_per_item, void* stream);
 int bd_dconv_expand_update(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
                            const float* beta1, const float* w2t, const float* b2, const float* mean_rstd2,
                            const float* gamma2, const float* beta2, const float* scale, float* x, long long M, int C,
-                           long long rows_per_item, int slabs_per_item, void* stream);
+                           long long rows_per_item, int slabs_per_item, int math, void* stream);
 /* DConv inner activation (demucs.py:138-139): h[m, c] = gelu(GroupNorm(h))[m, c] in place, slab map as
  * bd_dconv_tail.  Used by the tensor-core arm, whose TMA-fed A operand cannot be transformed on the fly. */
 int bd_gn_gelu_apply(float* h, const float* mean_rstd, const float* gamma, const float* beta, long long M, int C,

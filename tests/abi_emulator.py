@@ -213,7 +213,7 @@ def bd_dconv_expand_stats(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, gram_ws, M,
     np.add.at(st[:, 1], slab, (u64 ** 2).sum(1))
 
 
-def bd_dconv_expand_update(h, ldh, hid, mr1, g1, be1, w2t, b2, mr2, g2, be2, scale, x, M, Cc, rpi, spi, stream):
+def bd_dconv_expand_update(h, ldh, hid, mr1, g1, be1, w2t, b2, mr2, g2, be2, scale, x, M, Cc, rpi, spi, math_, stream):
     u, slab = _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi)
     st = f32(mr2, 2 * (int(slab.max()) + 1)).reshape(-1, 2)[slab]
     v = (u - st[:, :1]) * st[:, 1:2] * f32(g2, 2 * Cc) + f32(be2, 2 * Cc)
