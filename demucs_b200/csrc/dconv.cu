@@ -607,9 +607,131 @@ int launch_update_mma(const float* h, int ldh, const float* mr1, const float* g1
   return bd_check_launch("dconv_update_mma_kernel");
 }
 
+
+// ---- the dilated k=3 convolution of a narrow DConv layer (hid 6) on mma.sync fragments -------------------------
+// h[m, 0..5] = b1 + sum_tap W1[:, tap, :] . x[row of m shifted by (tap-1)*dil positions along the conv axis, :]
+// and (sum, sumsq) of h per GroupNorm slab.  [rows x 3C] x [3C x 6]: the output is so narrow that a tcgen05 tile
+// (N >= 16, its epilogue, a 16-wide padded h) costs more than the contraction.  Here the weights live in B
+// fragments, a warp takes 32 rows, every lane reads float4 runs of the input row (the K index is permuted so that
+// a lane's four fragment elements of two k-steps are one contiguous float4) and h is stored 8 floats wide.
+template <int C>
+__global__ void __launch_bounds__(256, 2) dconv_conv3_mma_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                              const float* __restrict__ b1, float* __restrict__ h,
+                                                              double* __restrict__ sums, long long M, long long rpi,
+                                                              int spi, int dil) {
+  constexpr int HID = 6, KSC = C / 8, NP = C / 16;            // k-steps / float4 pairs per tap
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  // B fragment of k-step (tap, 2p + s): b0 <- channel 16p + 4tig + 2s, b1 <- channel 16p + 4tig + 2s + 1; column gid
+  uint32_t bf[3 * KSC][2];
+#pragma unroll
+  for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+    for (int ks = 0; ks < KSC; ++ks) {
+      const int ch = 16 * (ks >> 1) + 4 * tig + 2 * (ks & 1);
+      bf[tap * KSC + ks][0] = gid < HID ? to_tf32(__ldg(w1 + (size_t)gid * 3 * C + tap * C + ch)) : 0u;
+      bf[tap * KSC + ks][1] = gid < HID ? to_tf32(__ldg(w1 + (size_t)gid * 3 * C + tap * C + ch + 1)) : 0u;
+    }
+  const float bz0 = 2 * tig < HID ? __ldg(b1 + 2 * tig) : 0.f, bz1 = 2 * tig + 1 < HID ? __ldg(b1 + 2 * tig + 1) : 0.f;
+  const long long T = rpi / spi;
+  const long long ntiles = (M + 31) / 32;
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
+    const long long m0 = tile * 32;
+    long long mrow[4];
+    int tpos[4];
+    bool live[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mrow[q] = m0 + gid + 8 * q;
+      live[q] = mrow[q] < M;
+      tpos[q] = (int)(((live[q] ? mrow[q] : m0) % rpi) / spi);
+    }
+    float c[2][4] = {{bz0, bz1, bz0, bz1}, {bz0, bz1, bz0, bz1}};
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      float4 v[4][NP];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long tt = tpos[q] + (long long)(tap - 1) * dil;
+        const bool ok = live[q] && tt >= 0 && tt < T;
+        const float* src = x + (mrow[q] + (long long)(tap - 1) * dil * spi) * C + 4 * tig;
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+          v[q][p] = ok ? __ldg(reinterpret_cast<const float4*>(src + 16 * p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          // rows 2f (gid + 16f) and 2f+1 (gid + 8 + 16f); a0/a1: k = tig of the two rows, a2/a3: k = tig + 4
+          const uint32_t a_even[4] = {to_tf32(v[2 * f][p].x), to_tf32(v[2 * f + 1][p].x), to_tf32(v[2 * f][p].y),
+                                      to_tf32(v[2 * f + 1][p].y)};
+          const uint32_t a_odd[4] = {to_tf32(v[2 * f][p].z), to_tf32(v[2 * f + 1][p].z), to_tf32(v[2 * f][p].w),
+                                     to_tf32(v[2 * f + 1][p].w)};
+          mma_tf32_16x8x8(c[f], a_even, bf[tap * KSC + 2 * p][0], bf[tap * KSC + 2 * p][1]);
+          mma_tf32_16x8x8(c[f], a_odd, bf[tap * KSC + 2 * p + 1][0], bf[tap * KSC + 2 * p + 1][1]);
+        }
+      }
+    }
+    // c[f] = {row gid+16f: cols 2tig, 2tig+1; row gid+8+16f: cols 2tig, 2tig+1}
+    long long slab[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int f = q >> 1, hi8 = q & 1;
+      const float h0 = c[f][2 * hi8], h1 = c[f][2 * hi8 + 1];
+      if (live[q]) *reinterpret_cast<float2*>(h + mrow[q] * 8 + 2 * tig) = make_float2(h0, h1);
+      float rs = h0 + h1, rq = fmaf(h0, h0, h1 * h1);          // padding columns are exactly zero
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rq += __shfl_xor_sync(0xffffffffu, rq, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      rq += __shfl_xor_sync(0xffffffffu, rq, 2);
+      const long long mm = live[q] ? mrow[q] : m0;
+      slab[q] = (mm / rpi) * spi + (mm % spi);
+      c[f][2 * hi8] = live[q] ? rs : 0.f;                        // reuse the accumulator registers for the row sums
+      c[f][2 * hi8 + 1] = live[q] ? rq : 0.f;
+    }
+    // one slab for the whole tile (time branch, away from item boundaries): one atomic pair per warp
+    const long long slab0 = __shfl_sync(0xffffffffu, slab[0], 0);
+    const bool uniform = __all_sync(0xffffffffu, slab[0] == slab0 && slab[1] == slab0 && slab[2] == slab0 && slab[3] == slab0);
+    if (uniform) {
+      float ws = 0.f, wq = 0.f;
+      if (tig == 0) {
+        ws = (c[0][0] + c[0][2]) + (c[1][0] + c[1][2]);
+        wq = (c[0][1] + c[0][3]) + (c[1][1] + c[1][3]);
+      }
+      ws = bd_warp_sum(ws);
+      wq = bd_warp_sum(wq);
+      if (lane == 0) {
+        atomicAdd(&sums[2 * slab0], (double)ws);
+        atomicAdd(&sums[2 * slab0 + 1], (double)wq);
+      }
+    } else if (tig == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (live[q]) {
+          atomicAdd(&sums[2 * slab[q]], (double)c[q >> 1][2 * (q & 1)]);
+          atomicAdd(&sums[2 * slab[q] + 1], (double)c[q >> 1][2 * (q & 1) + 1]);
+        }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int bd_dconv_conv3(const float* x, const float* w1, const float* b1, float* h, int ldh, double* sums1, long long M, int C,
+                   int hid, long long rows_per_item, int slabs_per_item, int dilation, void* stream) {
+  BD_REQUIRE(hid == 6 && C == 48 && ldh == 8, "bd_dconv_conv3: only hid 6 / C 48 / ldh 8 is built (hid=%d C=%d ldh=%d)", hid, C, ldh);
+  BD_REQUIRE(M > 0 && rows_per_item > 0 && slabs_per_item > 0 && rows_per_item % slabs_per_item == 0 && dilation > 0,
+             "bd_dconv_conv3: bad sizes");
+  BD_REQUIRE((((uintptr_t)x | (uintptr_t)h) & 15) == 0, "bd_dconv_conv3: unaligned tensor");
+  long long grid = ((M + 31) / 32 + 7) / 8;
+  if (grid > 148LL * 2 * 4) grid = 148LL * 2 * 4;     // 2 resident CTAs per SM, 4 rounds
+  dconv_conv3_mma_kernel<48><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, w1, b1, h, sums1, M, rows_per_item,
+                                                                                slabs_per_item, dilation);
+  return bd_check_launch("dconv_conv3_mma_kernel");
+}
 
 int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
                           const float* beta1, const float* w2t, const float* b2, double* sums2, double* gram_ws,

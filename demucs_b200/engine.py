@@ -262,7 +262,8 @@ class Engine:
         slabs = B * Fr
         stat = (T * Fr, Fr, Fr)                      # slab(m) = b*Fr + fr
         tc = self.mode != "fp32"
-        hp = (hid + 15) // 16 * 16 if tc else hid      # tensor-core arm: h is stored 16-column padded
+        narrow = self.mode == "tf32" and hid == 6 and C_ == 48     # dedicated mma.sync conv3, h stored 8 wide
+        hp = 8 if narrow else ((hid + 15) // 16 * 16 if tc else hid)   # tensor-core arm: h is 16-column padded
         h = self._buf(key, f"dconv_h{tag}", M * hp)
         sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64)
         mr1 = self._buf(key, f"dconv_mr1{tag}", 2 * slabs)
@@ -273,14 +274,19 @@ class Engine:
             dil = 2 ** dd
             # (1) h = conv3_dilated(x) and the GroupNorm statistics of h
             sums.zero_()
-            if Fr == 1:   # time branch: positions are the fast axis, one GroupNorm item per batch item
+            if narrow:
+                self._k("bd_dconv_conv3", ptr(x), ptr(W[f"{p}.w1"]), ptr(W[f"{p}.b1"]), ptr(h), hp, ptr(sums), M, C_, hid,
+                        T * Fr, Fr, dil, self._stream(), flops=2.0 * M * hid * 3 * C_, nbytes=4.0 * M * (C_ + hid),
+                        label="dconv_conv3_mma", detail=f"M={M} C={C_} hid={hid} dil={dil}")
+            elif Fr == 1:   # time branch: positions are the fast axis, one GroupNorm item per batch item
                 geo = dict(taps=((0, -dil), (0, 0), (0, dil)), I1=1, I0=T, J1=1, J0=T,
                            xs=(T * C_, 0, C_, 1), os_=(T * hp, 0, hp))
             else:         # frequency branch [B, T, Fr, C]: the conv runs along T, the slow axis
                 geo = dict(taps=((-dil, 0), (0, 0), (dil, 0)), I1=T, I0=Fr, J1=T, J0=Fr,
                            xs=(T * Fr * C_, Fr * C_, C_, 1), os_=(T * Fr * hp, Fr * hp, hp))
-            self._gemm(M=M, N=hp, Cin=C_, x=x, w=W[f"{p}.w1{sfx}"], bias=W[f"{p}.b1{sfx}"], out=h,
-                       stats_out=sums, stat=stat, tc=tc, **geo)
+            if not narrow:
+                self._gemm(M=M, N=hp, Cin=C_, x=x, w=W[f"{p}.w1{sfx}"], bias=W[f"{p}.b1{sfx}"], out=h,
+                           stats_out=sums, stat=stat, tc=tc, **geo)
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr1), slabs, float(T * hid), self._stream())
             # (2) statistics of u = conv1x1(gelu(gn(h))) WITHOUT storing u: the expanded [.., 2C] tensor never
             #     touches HBM, both passes recompute it from the 8x narrower h (csrc/dconv.cu)

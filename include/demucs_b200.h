@@ -131,6 +131,13 @@ int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float*
  *          derived from the slab's Gram matrix sum(g g^T): hid^2 instead of hid*2C products per row.
  * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place); math = BD_MATH_*: the
  *          BD_MATH_TF32 runs the expansion on mma.sync tf32 fragments, the other modes in exact fp32 */
+/* DConv dilated k=3 convolution of a narrow layer (demucs.py:138, hid = C/8 = 6) with its GroupNorm statistics,
+ * on mma.sync tf32 fragments (BD_MATH_TF32 class arithmetic).  x [M, C] rows in memory order, the conv axis is
+ * the position t = (m % rows_per_item) / slabs_per_item, neighbours are dilation * slabs_per_item rows away and
+ * read as zero outside the item.  w1 [hid, 3*C] tap-major, h [M, ldh = 8] (columns hid.. are written as zero),
+ * sums1[slab] += (sum, sumsq) of h; slab map as bd_dconv_tail.  Only hid 6 / C 48 is built. */
+int bd_dconv_conv3(const float* x, const float* w1, const float* b1, float* h, int ldh, double* sums1, long long M, int C,
+                   int hid, long long rows_per_item, int slabs_per_item, int dilation, void* stream);
 int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
                           const float* beta1, const float* w2t, const float* b2, double* sums2, double* gram_ws,
                           long long M, int C, long long rows_per_item, int slabs_per_item, void* stream);

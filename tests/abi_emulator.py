@@ -205,6 +205,28 @@ def _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi):
     return u.astype(np.float32), slab
 
 
+def bd_dconv_conv3(x, w1, b1, h, ldh, sums1, M, Cc, hid, rpi, spi, dil, stream):
+    xv = f32(x, M * Cc).reshape(M, Cc)
+    w = f32(w1, hid * 3 * Cc).reshape(hid, 3, Cc)
+    m = np.arange(M)
+    t = (m % rpi) // spi
+    T = rpi // spi
+    acc = np.tile(f32(b1, hid), (M, 1)).astype(np.float32)
+    for tap in range(3):
+        tt = t + (tap - 1) * dil
+        ok = (tt >= 0) & (tt < T)
+        src = np.where(ok, m + (tap - 1) * dil * spi, 0)
+        acc += np.where(ok[:, None], xv[src], 0.0) @ w[:, tap].T
+    hv = f32(h, M * ldh).reshape(M, ldh)
+    hv[:, :hid] = acc
+    hv[:, hid:] = 0.0
+    slab = (m // rpi) * spi + (m % spi)
+    st = f64(sums1, 2 * (int(slab.max()) + 1)).reshape(-1, 2)
+    a64 = acc.astype(np.float64)
+    np.add.at(st[:, 0], slab, a64.sum(1))
+    np.add.at(st[:, 1], slab, (a64 ** 2).sum(1))
+
+
 def bd_dconv_expand_stats(h, ldh, hid, mr1, g1, be1, w2t, b2, sums2, gram_ws, M, Cc, rpi, spi, stream):
     u, slab = _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi)
     st = f64(sums2, 2 * (int(slab.max()) + 1)).reshape(-1, 2)

@@ -89,3 +89,31 @@ def test_tf32_arm_really_ran():
     b, _, _, _ = run_plain(2688, 512, 512, _lib.MATH_TF32)
     e = rel_l2(b.cpu(), a.cpu())
     assert 1e-5 < e < 1.5e-3
+
+
+@pytest.mark.parametrize("Fr,dil", [(1, 1), (1, 2), (8, 1), (32, 2)])
+def test_dconv_conv3_mma(Fr, dil):
+    """Dedicated narrow DConv conv3 (mma.sync tf32 fragments) against an fp64 conv along the position axis,
+    including the per-slab statistics; ragged row count (not a multiple of 32)."""
+    B, T, C, hid = 3, 37, 48, 6
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, Fr, C, generator=g)
+    w = torch.randn(hid, C, 3, generator=g) / (3 * C) ** 0.5
+    b = torch.randn(hid, generator=g)
+    w1 = w.permute(0, 2, 1).reshape(hid, 3 * C).contiguous()          # tap-major
+    M = B * T * Fr
+    xd, w1d, bd = x.to(DEV), w1.to(DEV), b.to(DEV)
+    h = torch.full((M, 8), float("nan"), device=DEV)
+    sums = torch.zeros(B * Fr, 2, dtype=torch.float64, device=DEV)
+    _lib.call("bd_dconv_conv3", xd.data_ptr(), w1d.data_ptr(), bd.data_ptr(), h.data_ptr(), 8, sums.data_ptr(), M, C, hid,
+              T * Fr, Fr, dil, 0)
+    torch.cuda.synchronize()
+    xin = x.double().permute(0, 2, 3, 1).reshape(B * Fr, C, T)           # the reference's [(b f), c, t] view
+    want = torch.nn.functional.conv1d(xin, w.double(), b.double(), padding=dil, dilation=dil)   # [(b f), hid, T]
+    want_rows = want.reshape(B, Fr, hid, T).permute(0, 3, 1, 2).reshape(M, hid)
+    got = h.cpu()
+    assert torch.all(got[:, hid:] == 0)
+    assert rel_l2(got[:, :hid], want_rows.float()) < 2e-3              # single-pass tf32
+    s = want.reshape(B * Fr, -1)
+    assert torch.allclose(sums[:, 0].cpu(), s.sum(1), rtol=0, atol=0.1)
+    assert torch.allclose(sums[:, 1].cpu(), (s ** 2).sum(1), rtol=5e-3)

@@ -89,3 +89,23 @@ def test_tensor_chunk_and_center_trim_follow_reference_semantics():
     assert D.center_trim(x, 15)[0, 0].tolist() == list(range(2, 17))  # odd surplus trimmed on the right
     with pytest.raises(ValueError):
         D.center_trim(x, 21)
+
+
+def test_emulated_dconv_conv3_is_the_dilated_conv():
+    """The numpy statement of bd_dconv_conv3 (full-size layers only, so the small-model tests never reach it)."""
+    import numpy as np
+    import abi_emulator as E
+    B, T, Fr, C, hid, dil = 2, 11, 4, 48, 6, 2
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, T, Fr, C, generator=g)
+    w = torch.randn(hid, C, 3, generator=g)
+    b = torch.randn(hid, generator=g)
+    w1 = w.permute(0, 2, 1).reshape(hid, 3 * C).contiguous()
+    M = B * T * Fr
+    h = torch.zeros(M, 8)
+    sums = torch.zeros(B * Fr, 2, dtype=torch.float64)
+    E.bd_dconv_conv3(x.data_ptr(), w1.data_ptr(), b.data_ptr(), h.data_ptr(), 8, sums.data_ptr(), M, C, hid, T * Fr, Fr, dil, 0)
+    want = torch.nn.functional.conv1d(x.permute(0, 2, 3, 1).reshape(B * Fr, C, T), w, b, padding=dil, dilation=dil)
+    rows = want.reshape(B, Fr, hid, T).permute(0, 3, 1, 2).reshape(M, hid)
+    assert rel_l2(h[:, :hid], rows) < 1e-5
+    assert np.allclose(sums[:, 0].numpy(), want.reshape(B * Fr, -1).double().sum(1).numpy(), atol=1e-3)
