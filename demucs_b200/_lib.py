@@ -61,6 +61,7 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_conv_gemm_arm": [C.POINTER(GemmDesc)],
     "bd_finalize_group_stats": [_P, _P, _I, _D, _P],
     "bd_dconv_tail": [_P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
+    "bd_encoder_conv0": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bd_dconv_conv3": [_P, _P, _P, _P, _I, _P, _LL, _I, _I, _LL, _I, _I, _P],
     "bd_dconv_expand_stats": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "bd_dconv_expand_update": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _I, _P],

@@ -716,9 +716,122 @@ __global__ void __launch_bounds__(256, 2) dconv_conv3_mma_kernel(const float* __
   }
 }
 
+
+// ---- first encoder layer of each branch: Conv(k=8, s=4, p=2) over 2 / 4 input channels -> 48, GELU ---------------
+// (hdemucs.py:110,139-144 with the input normalisation htdemucs.py:545-554 folded into the load).  K = 8 taps x C_in
+// = 16 / 32 is too short for a tcgen05 tile; on mma.sync fragments the weights (48 x K) live in registers, a warp
+// takes 32 output positions, and bias + GELU happen on the accumulator fragment.
+//   CM = false (frequency branch): x [B, I1, Jin, 4] channels-last, the window of output i0 is the 32 contiguous
+//        floats starting at position 4*i0 - 2; K index permuted so that a lane reads float4 = one position.
+//   CM = true  (time branch):      x [B, 2, Jin] channel-major (the raw mix), k-step = channel, k = tap.
+// Positions outside [0, Jin) read as zero AFTER the normalisation (zero padding of the normalised tensor).
+template <int CIN, bool CM>
+__global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __restrict__ x, const float* __restrict__ norm,
+                                                                int norm_stride, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ out,
+                                                                long long M, int I1, int Io, int Jin) {
+  constexpr int K = 8 * CIN, KS = K / 8, NT = 6, COUT = 48;
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  // logical k of fragment element (ks, tig, half) -> (tap, channel)
+  //   CM:  ks = channel, tap = tig + 4*half
+  //   !CM: pair p = ks>>1, position-in-window = 4p + tig (one float4 = 4 channels), channel = 2*(ks&1) + half
+  uint32_t bf[KS][NT][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int tap = CM ? tig + 4 * half : 4 * (ks >> 1) + tig;
+        const int ch = CM ? ks : 2 * (ks & 1) + half;
+        bf[ks][nt][half] = to_tf32(__ldg(w + (size_t)(8 * nt + gid) * K + tap * CIN + ch));
+      }
+  float bz[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    bz[nt][0] = __ldg(bias + 8 * nt + 2 * tig);
+    bz[nt][1] = __ldg(bias + 8 * nt + 2 * tig + 1);
+  }
+  const long long rows_per_item = (long long)I1 * Io;
+  const long long ntiles = (M + 31) / 32;
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
+    const long long m0 = tile * 32;
+    uint32_t a[2][KS][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long m = m0 + gid + 8 * q;
+      const long long mm = m < M ? m : m0;
+      const int b = (int)(mm / rows_per_item);
+      const long long r = mm - (long long)b * rows_per_item;
+      const int i1 = (int)(r / Io), i0 = (int)(r - (long long)i1 * Io);
+      const float mean = __ldg(norm + (size_t)b * norm_stride), rstd = __ldg(norm + (size_t)b * norm_stride + 2);
+      const int f = q >> 1, hi8 = q & 1;
+      if (CM) {
+        const float* src = x + (size_t)b * CIN * Jin;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int pos = 4 * i0 - 2 + tig + 4 * half;
+            const float v = (pos >= 0 && pos < Jin) ? (__ldg(src + (size_t)ks * Jin + pos) - mean) * rstd : 0.f;
+            a[f][ks][2 * half + hi8] = to_tf32(v);
+          }
+      } else {
+        const float* src = x + (((size_t)b * I1 + i1) * Jin) * CIN;
+#pragma unroll
+        for (int p = 0; p < KS / 2; ++p) {
+          const int pos = 4 * i0 - 2 + 4 * p + tig;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pos >= 0 && pos < Jin) {
+            v = __ldg(reinterpret_cast<const float4*>(src + (size_t)pos * CIN));
+            v = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+          }
+          a[f][2 * p][hi8] = to_tf32(v.x);          // ks = 2p:   channels 0 (half 0), 1 (half 1)
+          a[f][2 * p][2 + hi8] = to_tf32(v.y);
+          a[f][2 * p + 1][hi8] = to_tf32(v.z);      // ks = 2p+1: channels 2, 3
+          a[f][2 * p + 1][2 + hi8] = to_tf32(v.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        float c[4] = {bz[nt][0], bz[nt][1], bz[nt][0], bz[nt][1]};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_16x8x8(c, a[f][ks], bf[ks][nt][0], bf[ks][nt][1]);
+#pragma unroll
+        for (int hi8 = 0; hi8 < 2; ++hi8) {
+          const long long m = m0 + gid + 8 * (2 * f + hi8);
+          if (m < M)
+            *reinterpret_cast<float2*>(out + m * COUT + 8 * nt + 2 * tig) =
+                make_float2(bd_gelu(c[2 * hi8]), bd_gelu(c[2 * hi8 + 1]));
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int bd_encoder_conv0(const float* x, int channel_major, const float* norm, int norm_stride, const float* w, const float* bias,
+                     float* out, int B, int I1, int Io, int Jin, int cin, int cout, void* stream) {
+  BD_REQUIRE(cout == 48 && ((channel_major && cin == 2 && I1 == 1) || (!channel_major && cin == 4)),
+             "bd_encoder_conv0: only the htdemucs first layers are built (cin=%d cout=%d channel_major=%d)", cin, cout, channel_major);
+  BD_REQUIRE(B > 0 && I1 > 0 && Io > 0 && Jin > 0 && 4 * (Io - 1) - 2 < Jin, "bd_encoder_conv0: bad sizes");
+  BD_REQUIRE((((uintptr_t)x | (uintptr_t)out) & 15) == 0, "bd_encoder_conv0: unaligned tensor");
+  const long long M = (long long)B * I1 * Io;
+  long long grid = ((M + 31) / 32 + 7) / 8;
+  if (grid > 148LL * 2 * 4) grid = 148LL * 2 * 4;
+  if (channel_major)
+    conv_first_mma_kernel<2, true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
+  else
+    conv_first_mma_kernel<4, false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
+  return bd_check_launch("conv_first_mma_kernel");
+}
 
 int bd_dconv_conv3(const float* x, const float* w1, const float* b1, float* h, int ldh, double* sums1, long long M, int C,
                    int hid, long long rows_per_item, int slabs_per_item, int dilation, void* stream) {

@@ -435,7 +435,14 @@ class Engine:
             y = self._buf(key, "y_t", B * Tout * Cc)
             first = i == 0
             Tin_p = Tin if first else tp(Tin)
-            self._gemm(M=B * Tout, N=Cc, Cin=Cin_t, x=xt, w=W[f"tencoder.{i}.conv.w"], bias=W[f"tencoder.{i}.conv.b"],
+            conv0 = first and self.mode == "tf32" and Cc == 48 and A == 2     # dedicated mma.sync first-layer kernel
+            if conv0:
+                self._k("bd_encoder_conv0", ptr(xt), 1, norm.data_ptr() + 16, 8, ptr(W[f"tencoder.{i}.conv.w"]),
+                        ptr(W[f"tencoder.{i}.conv.b"]), ptr(y), B, 1, Tout, L, A, Cc, self._stream(),
+                        flops=2.0 * B * Tout * Cc * 8 * A, nbytes=4.0 * B * (A * L + Tout * Cc), label="encoder_conv0_mma",
+                        detail=f"M={B * Tout} cin={A}")
+            else:
+              self._gemm(M=B * Tout, N=Cc, Cin=Cin_t, x=xt, w=W[f"tencoder.{i}.conv.w"], bias=W[f"tencoder.{i}.conv.b"],
                        out=y, taps=tuple((0, k - 2) for k in range(8)), I1=1, I0=Tout, m0=4, J1=1, J0=Tin_p,
                        xs=(A * L, 0, 1, L) if first else (Tin_p * Cin_t, 0, Cin_t, 1), os_=(Tout * Cc, 0, Cc),
                        a_mode=_lib.A_ITEM_AFFINE if first else _lib.A_NONE,
@@ -453,7 +460,13 @@ class Engine:
             # frequency branch: Conv2d(k=(8,1),s=(4,1),p=(2,0)) -> GELU
             Fo = Fin // 4
             y = self._buf(key, "y_f", B * T * Fo * Cc)
-            self._gemm(M=B * T * Fo, N=Cc, Cin=Cin, x=xf, w=W[f"encoder.{i}.conv.w"], bias=W[f"encoder.{i}.conv.b"],
+            if conv0 and Cin == 4:
+                self._k("bd_encoder_conv0", ptr(xf), 0, ptr(norm), 8, ptr(W[f"encoder.{i}.conv.w"]),
+                        ptr(W[f"encoder.{i}.conv.b"]), ptr(y), B, T, Fo, Fin, Cin, Cc, self._stream(),
+                        flops=2.0 * B * T * Fo * Cc * 8 * Cin, nbytes=4.0 * B * T * (Fin * Cin + Fo * Cc),
+                        label="encoder_conv0_mma", detail=f"M={B * T * Fo} cin={Cin}")
+            else:
+              self._gemm(M=B * T * Fo, N=Cc, Cin=Cin, x=xf, w=W[f"encoder.{i}.conv.w"], bias=W[f"encoder.{i}.conv.b"],
                        out=y, taps=tuple((0, k - 2) for k in range(8)), I1=T, I0=Fo, m0=4, J1=T, J0=Fin,
                        xs=(T * Fin * Cin, Fin * Cin, Cin, 1), os_=(T * Fo * Cc, Fo * Cc, Cc),
                        a_mode=_lib.A_ITEM_AFFINE if first else _lib.A_NONE,

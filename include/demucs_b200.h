@@ -131,6 +131,14 @@ int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float*
  *          derived from the slab's Gram matrix sum(g g^T): hid^2 instead of hid*2C products per row.
  * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place); math = BD_MATH_*: the
  *          BD_MATH_TF32 runs the expansion on mma.sync tf32 fragments, the other modes in exact fp32 */
+/* First encoder layer of a branch (hdemucs.py:110,139-144): out = gelu(conv_{k=8,s=4,p=2}((x - mean_b) * rstd_b) + bias)
+ * with the per-item input normalisation (htdemucs.py:545-554) folded into the load; positions outside [0, Jin) are
+ * zero AFTER normalisation.  mean_b = norm[b*norm_stride], rstd_b = norm[b*norm_stride + 2] (bd_finalize_item_norm).
+ *   channel_major = 0: x [B, I1, Jin, cin] channels-last (spectrogram, cin = 4);  = 1: x [B, cin, Jin] (the mix, cin = 2,
+ *   I1 = 1).  w [cout, 8*cin] tap-major, out [B, I1, Io, cout].  mma.sync tf32 fragments (BD_MATH_TF32 class);
+ *   only cout = 48 is built. */
+int bd_encoder_conv0(const float* x, int channel_major, const float* norm, int norm_stride, const float* w, const float* bias,
+                     float* out, int B, int I1, int Io, int Jin, int cin, int cout, void* stream);
 /* DConv dilated k=3 convolution of a narrow layer (demucs.py:138, hid = C/8 = 6) with its GroupNorm statistics,
  * on mma.sync tf32 fragments (BD_MATH_TF32 class arithmetic).  x [M, C] rows in memory order, the conv axis is
  * the position t = (m % rows_per_item) / slabs_per_item, neighbours are dilation * slabs_per_item rows away and

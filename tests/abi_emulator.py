@@ -205,6 +205,25 @@ def _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi):
     return u.astype(np.float32), slab
 
 
+def bd_encoder_conv0(x, channel_major, norm, norm_stride, w, bias, out, B, I1, Io, Jin, cin, cout, stream):
+    nv = f32(norm, (B - 1) * norm_stride + 3)
+    wv = f32(w, cout * 8 * cin).reshape(cout, 8, cin)
+    ov = f32(out, B * I1 * Io * cout).reshape(B, I1, Io, cout)
+    if channel_major:
+        xv = f32(x, B * cin * Jin).reshape(B, 1, cin, Jin).transpose(0, 1, 3, 2)      # [B, 1, Jin, cin]
+    else:
+        xv = f32(x, B * I1 * Jin * cin).reshape(B, I1, Jin, cin)
+    for b in range(B):
+        mean, rstd = nv[b * norm_stride], nv[b * norm_stride + 2]
+        xn = np.zeros((I1, 4 * Io + 8, cin), np.float32)                           # window of i0: rows 4*i0 .. 4*i0+7
+        hi = min(Jin, 4 * Io + 6)
+        xn[:, 2:2 + hi] = (xv[b, :, :hi] - mean) * rstd
+        acc = np.tile(f32(bias, cout), (I1, Io, 1)).astype(np.float32)
+        for tap in range(8):
+            acc += xn[:, tap:tap + 4 * Io:4] @ wv[:, tap].T
+        ov[b] = gelu(acc)
+
+
 def bd_dconv_conv3(x, w1, b1, h, ldh, sums1, M, Cc, hid, rpi, spi, dil, stream):
     xv = f32(x, M * Cc).reshape(M, Cc)
     w = f32(w1, hid * 3 * Cc).reshape(hid, 3, Cc)

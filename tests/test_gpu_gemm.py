@@ -117,3 +117,37 @@ def test_dconv_conv3_mma(Fr, dil):
     s = want.reshape(B * Fr, -1)
     assert torch.allclose(sums[:, 0].cpu(), s.sum(1), rtol=0, atol=0.1)
     assert torch.allclose(sums[:, 1].cpu(), (s ** 2).sum(1), rtol=5e-3)
+
+
+@pytest.mark.parametrize("channel_major", [0, 1])
+def test_encoder_conv0_mma(channel_major):
+    """First encoder layer (k=8, s=4, p=2, normalisation folded in, GELU) on mma.sync fragments vs torch fp64."""
+    g = torch.Generator().manual_seed(9)
+    B, cout = 3, 48
+    if channel_major:
+        cin, I1, Jin = 2, 1, 1003
+        x = torch.randn(B, cin, Jin, generator=g)
+        xin = x.double()                                                    # [B, cin, Jin]
+    else:
+        cin, I1, Jin = 4, 5, 64
+        x = torch.randn(B, I1, Jin, cin, generator=g)
+        xin = x.double().permute(0, 1, 3, 2).reshape(B * I1, cin, Jin)
+    Io = (Jin + 3) // 4
+    w = torch.randn(cout, cin, 8, generator=g) / (8 * cin) ** 0.5
+    b = torch.randn(cout, generator=g)
+    norm = torch.zeros(B, 8)
+    norm[:, 0] = torch.randn(B, generator=g) * 0.1
+    norm[:, 2] = 1.0 + 0.2 * torch.rand(B, generator=g)
+    wp = w.permute(0, 2, 1).reshape(cout, 8 * cin).contiguous()
+    out = torch.full((B, I1, Io, cout), float("nan"), device=DEV)
+    xd, nd, wd, bd = x.to(DEV), norm.to(DEV), wp.to(DEV), b.to(DEV)
+    _lib.call("bd_encoder_conv0", xd.data_ptr(), channel_major, nd.data_ptr(), 8, wd.data_ptr(), bd.data_ptr(),
+              out.data_ptr(), B, I1, Io, Jin, cin, cout, 0)
+    torch.cuda.synchronize()
+    rep = I1 if not channel_major else 1
+    mean = norm[:, 0].double().repeat_interleave(rep).view(-1, 1, 1)
+    rstd = norm[:, 2].double().repeat_interleave(rep).view(-1, 1, 1)
+    xn = F.pad((xin - mean) * rstd, (2, 4 * Io + 4 - Jin + 2))              # zero pad AFTER normalisation
+    want = F.gelu(F.conv1d(xn, w.double(), b.double(), stride=4))[..., :Io]  # [B*I1, cout, Io]
+    want = want.reshape(B, I1, cout, Io).permute(0, 1, 3, 2)
+    assert rel_l2(out.cpu(), want.float()) < 2e-3

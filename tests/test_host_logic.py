@@ -109,3 +109,27 @@ def test_emulated_dconv_conv3_is_the_dilated_conv():
     rows = want.reshape(B, Fr, hid, T).permute(0, 3, 1, 2).reshape(M, hid)
     assert rel_l2(h[:, :hid], rows) < 1e-5
     assert np.allclose(sums[:, 0].numpy(), want.reshape(B * Fr, -1).double().sum(1).numpy(), atol=1e-3)
+
+
+@pytest.mark.parametrize("channel_major", [0, 1])
+def test_emulated_encoder_conv0(channel_major):
+    """The numpy statement of bd_encoder_conv0 (htdemucs first layers only; the small test model never reaches it)."""
+    import abi_emulator as E
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    B, cout = 2, 48
+    cin, I1, Jin = (2, 1, 101) if channel_major else (4, 3, 32)
+    x = torch.randn(B, cin, Jin, generator=g) if channel_major else torch.randn(B, I1, Jin, cin, generator=g)
+    xin = x if channel_major else x.permute(0, 1, 3, 2).reshape(B * I1, cin, Jin)
+    Io = (Jin + 3) // 4
+    w = torch.randn(cout, cin, 8, generator=g)
+    b = torch.randn(cout, generator=g)
+    norm = torch.zeros(B, 8)
+    norm[:, 0], norm[:, 2] = 0.3, 1.7
+    wp = w.permute(0, 2, 1).reshape(cout, 8 * cin).contiguous()
+    out = torch.zeros(B, I1, Io, cout)
+    E.bd_encoder_conv0(x.data_ptr(), channel_major, norm.data_ptr(), 8, wp.data_ptr(), b.data_ptr(), out.data_ptr(),
+                       B, I1, Io, Jin, cin, cout, 0)
+    xn = F.pad((xin - 0.3) * 1.7, (2, 4 * Io + 6 - Jin))
+    want = F.gelu(F.conv1d(xn, w, b, stride=4))[..., :Io].reshape(B, I1, cout, Io).permute(0, 1, 3, 2)
+    assert rel_l2(out, want) < 1e-5
