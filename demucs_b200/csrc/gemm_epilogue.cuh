@@ -39,7 +39,7 @@ __device__ __forceinline__ EpiRow bd_epi_row(const bd_gemm_desc& d, long long m6
 }
 
 // Can every epilogue operand be accessed as aligned float4 (float2 after GLU)?  Uniform per launch.
-__device__ __forceinline__ bool bd_epi_vec_ok(const bd_gemm_desc& d) {
+__host__ __device__ __forceinline__ bool bd_epi_vec_ok(const bd_gemm_desc& d) {
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
   bool ok = d.N % 4 == 0 && d.os_0 % 4 == 0 && d.os_1 % 4 == 0 && d.os_b % 4 == 0;
   ok = ok && al16(d.out) && al16(d.bias) && al16(d.rowbias) && al16(d.resid) && al16(d.scale) && al16(d.addend) &&

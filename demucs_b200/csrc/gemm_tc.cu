@@ -385,7 +385,8 @@ struct PCfg {
   // (TBN <= 32, the epilogue of one tile is too small to share): each group takes every kPGroups-th TILE
   static constexpr bool kTileSplit = TBN <= 32;
   static constexpr int kNAcc = kTileSplit ? kPGroups : 2;
-  static constexpr int kWarpCols = kTileSplit ? TBN : TBN / kPGroups;
+  static constexpr int kHalves = TBN > 128 ? 2 : 1;            // 256-column tiles: the epilogue works on 128 at a time
+  static constexpr int kWarpCols = kTileSplit ? TBN : (TBN / kHalves) / kPGroups;
   static constexpr int kStagingBytes = 4 * kPGroups * 32 * (kWarpCols + 4) * 4;
   static constexpr int kTailBytes = 512 + 128 * kPGroups * 32;   // barriers + TMEM slot, then the row tables
   static constexpr int kBudget = 227 * 1024 - 1024 - kTailBytes - kStagingBytes;
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
   uint64_t* empty_bar = full_bar + kStages;
   constexpr int kNAcc = C_::kNAcc;
   constexpr bool kTileSplit = C_::kTileSplit;
+  constexpr int NH = C_::kHalves;
   uint64_t* tmem_full = empty_bar + kStages;       // [kNAcc]
   uint64_t* tmem_empty = tmem_full + kNAcc;        // [kNAcc]
   uint64_t* conv_bar = tmem_empty + kNAcc;             // [kStages] X3: hi/lo tiles written by the splitter warps
@@ -590,9 +592,17 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
           asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
         }
       }
-      mbar_wait_relaxed(&tmem_full[a], (uint32_t)((tcount / kNAcc) & 1));
-      tcgen05_fence_after();
-      const uint32_t acc = tmem_base + (uint32_t)(a * TBN + cbase) + ((uint32_t)(quarter * 32) << 16);
+      // a 256-column tile is finished as two 128-column halves (one staging buffer serves both)
+      for (int half = 0; half < NH; ++half) {
+      const int n0h = n0 + 128 * half;
+      if (half == 0) {
+        mbar_wait_relaxed(&tmem_full[a], (uint32_t)((tcount / kNAcc) & 1));
+        tcgen05_fence_after();
+      } else {
+        __syncwarp();                              // the staging rows of the first half have been consumed
+      }
+      const bool last_half = half == NH - 1;
+      const uint32_t acc = tmem_base + (uint32_t)(a * TBN + 128 * half + cbase) + ((uint32_t)(quarter * 32) << 16);
       if (vec) {
         rinfo[lane].obase = er.obase;
         rinfo[lane].i0 = row_ok ? er.i0 : -1;
@@ -600,7 +610,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
         rinfo[lane].e_mean = er.e_mean;
         rinfo[lane].e_rstd = er.e_rstd;
         for (int c0 = 0; c0 < WC; c0 += CW) {
-          if (n0 + cbase + c0 >= d.N) break;
+          if (n0h + cbase + c0 >= d.N) break;
           uint32_t v[CW];
           if constexpr (CW == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
 #pragma unroll
@@ -611,10 +621,10 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[a]);   // accumulator is free for tile i+2 while we finish tile i
+        if (lane == 0 && last_half) mbar_arrive(&tmem_empty[a]);   // accumulator is free for tile i+2 while we finish tile i
         if (fast >= 0) {
           const uint32_t st_s = smem_u32(stage), ri_s = smem_u32(rinfo);
-          const int n0w = n0 + cbase;
+          const int n0w = n0h + cbase;
           constexpr int FRB = kPGroups >= 4 ? 2 : 4;
           switch (fast) {
             case 0: epi_fast_rows<BD_ACT_NONE, false, false, false, false, WC, FRB>(d, st_s, ri_s, lane, n0w, ssum, ssq); break;
@@ -631,7 +641,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
         constexpr int RPI = 32 / CG;
         constexpr int RB = kPGroups >= 4 ? 2 : 4;
         const int cg = lane % CG, rsub = lane / CG;
-        const int n = n0 + cbase + 4 * cg;
+        const int n = n0h + cbase + 4 * cg;
         const bool col_ok = n < d.N;
         EpiCol ecol;
         if (col_ok) ecol = bd_epi_cols4(d, n);
@@ -689,13 +699,13 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
         }
       } else {
         for (int c0 = 0; c0 < WC; c0 += CW) {
-          if (n0 + cbase + c0 >= d.N) break;
+          if (n0h + cbase + c0 >= d.N) break;
           uint32_t v[CW];
           if constexpr (CW == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
-              const int n = n0 + cbase + c0 + j;
+              const int n = n0h + cbase + c0 + j;
               if (n < d.N) {
                 float st;
                 if (bd_epi_apply(d, er, n, __uint_as_float(v[j]), __uint_as_float(v[(j + 1) % CW]), st)) {
@@ -708,12 +718,13 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, X3>::kThreads), 1) conv_gemm_t
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[a]);
+        if (lane == 0 && last_half) mbar_arrive(&tmem_empty[a]);
         if (row_stats && row_ok) {
           atomicAdd(&d.stats_out[2 * (size_t)my_slab], (double)ssum);
           atomicAdd(&d.stats_out[2 * (size_t)my_slab + 1], (double)ssq);
         }
       }
+      }   // half
       if (d.stats_out && d.stat_mod == 1) {   // one slab per tile (host guarantee): one atomic pair per warp
         const double ds = bd_warp_sum_d((double)ssum), dq = bd_warp_sum_d((double)ssq);
         if (lane == 0) {
@@ -843,6 +854,22 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   int rc;
   const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
   const cudaStream_t st = (cudaStream_t)stream;
+  // 256-column tiles for the long-K GEMMs whose epilogue has a compile-time form: one 128x256x8 MMA reads 12 KB of
+  // shared memory for the work of two 128x128x8 MMAs (16 KB) -- the tf32 kernel is operand-bandwidth-bound
+  static const bool wide_ok = getenv("BD_TC_NO_WIDE") == nullptr;
+  const bool wide = wide_ok && d.math == BD_MATH_TF32 && d.N % 256 == 0 && d.K >= 256 && d.out && !d.convt && !d.oc_split &&
+                    !d.rowbias && !d.addend && !d.e_stats && (!d.stats_out || d.stat_mod == 1) && bd_epi_vec_ok(d);
+  // ... unless the halved tile count quantises badly over the SMs (short M, N = 512: 2.3 waves instead of 4.5)
+  auto wave_eff = [&](int tile_n) {
+    const long long t = (long long)items * g.blocks1 * g.blocks0 * ((d.N + tile_n - 1) / tile_n);
+    return (double)t / (double)(((t + 147) / 148) * 148);
+  };
+  if (wide && wave_eff(256) >= wave_eff(128) - 0.05) {
+    g.cpb = d.Cin / 16;
+    rc = launch_tc_persist<16, 256, false>(d, g, items, st);
+    *handled = 1;
+    return rc;
+  }
 #define BD_TC_PERSIST(TBK_, X3_)                                                                               \
   (tbn == 16 ? launch_tc_persist<TBK_, 16, X3_>(d, g, items, st) : tbn == 32 ? launch_tc_persist<TBK_, 32, X3_>(d, g, items, st) \
    : tbn == 64 ? launch_tc_persist<TBK_, 64, X3_>(d, g, items, st) : launch_tc_persist<TBK_, 128, X3_>(d, g, items, st))
