@@ -48,6 +48,18 @@ def test_stft_istft_kernels(L):
     torch.cuda.synchronize()
     want = stft_cac(x.double())
     got = spec.permute(0, 3, 2, 1).cpu()
+    if rel_l2(got, want) >= 1e-5:      # diagnostics: where does it differ?
+        err = (got.double() - want).abs()          # [B, 4, F, T]
+        bad = (err > 1e-4 * want.abs().max()).nonzero()
+        print("STFT mismatch:", rel_l2(got, want), "bad elements:", bad.shape[0], "first:", bad[:12].tolist(),
+              "frames:", sorted(set(bad[:, 3].tolist()))[:20], "max err", float(err.max()), "max ref", float(want.abs().max()))
+        spec2 = torch.empty_like(spec)
+        st2 = torch.zeros_like(stats)
+        _lib.call("bd_stft_cac", xd.data_ptr(), eng.window.data_ptr(), eng.twiddle.data_ptr(), spec2.data_ptr(),
+                  st2.data_ptr(), B, 2, L, 0)
+        torch.cuda.synchronize()
+        print("second run rel_l2:", rel_l2(spec2.permute(0, 3, 2, 1).cpu(), want), "window/twiddle checksums",
+              float(eng.window.double().sum()), float(eng.twiddle.double().abs().sum()))
     assert rel_l2(got, want) < 1e-5
     assert float((got.double() - want).abs().max() / want.abs().max()) < 1e-5   # bins, max-abs flavour
     st = stats.view(B, 4).cpu()
