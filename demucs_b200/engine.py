@@ -200,10 +200,10 @@ class Engine:
         return t[:numel]
 
     def _k(self, name: str, *args, flops: float = 0.0, nbytes: float = 0.0, label: tp.Optional[str] = None,
-           detail: str = "") -> None:
+           detail: str = "", kernels: int = 1) -> None:
         """Launch one kernel through the C ABI.  ``flops`` / ``nbytes`` are the ALGORITHMIC work of the
         launch, recorded with CUDA events when a profile is being taken."""
-        self.launches += 1
+        self.launches += kernels          # kernel launches behind this entry point (bench.py's gpu_launches)
         if self._prof is None:
             _lib.call(name, *args)
             return
@@ -296,7 +296,7 @@ class Engine:
             self._k("bd_dconv_expand_stats", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
                     ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(sums), ptr(gram), M, C_, T * Fr, Fr, self._stream(),
                     nbytes=4.0 * M * hid, flops=4.0 * M * hid * C_, label="dconv_expand_stats",
-                    detail=f"M={M} C={C_} hid={hid}")
+                    detail=f"M={M} C={C_} hid={hid}", kernels=2)
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr2), slabs, float(T * 2 * C_), self._stream())
             # (3) x += scale * GLU(gn(u)), in place: the dedicated kernels of csrc/dconv.cu (mma.sync fragments in
             #     "tf32" mode, exact FFMA otherwise).  The widest layers (hid 48; in "tf32x3" also hid 24) are a real
@@ -323,12 +323,13 @@ class Engine:
         nws = _lib.call_value("bd_attention_workspace", B, H, Tq, Tk, self._math())
         ws = self._buf(key, f"att_ws{tag}", nws) if nws else None
         label = "attention_simt" if self.mode == "fp32" else "attention_tc"
+        nk = {"fp32": 1, "tf32": 2, "tf32x3": 4}[self.mode]     # + V transpose (+ Q / K hi-lo splits)
         if kv_src is None:  # self attention: one packed projection
             qkv = self._buf(key, f"qkv{tag}", B * Tq * 3 * D)
             self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv)
             self._k("bd_attention", ptr(qkv), qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, ptr(att),
                     B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), ptr(ws), self._stream(),
-                    flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label=label)
+                    flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label=label, kernels=nk)
         else:
             q = self._buf(key, f"q{tag}", B * Tq * D)
             kv = self._buf(key, f"kv{tag}", B * Tk * 2 * D)
@@ -336,7 +337,7 @@ class Engine:
             self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv)
             self._k("bd_attention", ptr(q), ptr(kv), kv.data_ptr() + 4 * D, ptr(att),
                     B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), ptr(ws), self._stream(),
-                    flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label=label)
+                    flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label=label, kernels=nk)
         return att
 
     def _math(self) -> int:
