@@ -349,3 +349,20 @@ def test_full_size_batch_64_items_are_independent():
     for b in (0, 37, 63):
         one = eng.forward(mix[b:b + 1].contiguous())
         assert rel_l2(one.cpu(), full[b:b + 1].cpu()) < 2e-6, b
+
+
+def test_forward_htdemucs_short_input_batch3_tf32():
+    """The htdemucs geometry with an input shorter than the training segment (the model pads it, htdemucs.py:536-542)
+    and an odd batch, on the single-pass tensor-core arm: exercises the ragged tails of the mma.sync kernels."""
+    cfg = htdemucs_config()
+    W = init_weights(cfg, 4, layer_scale=0.5)
+    mix = synth_mix(3, 123457, 8)
+    eng = Engine(cfg, W, DEV, mode="tf32")
+    got = eng.forward(mix.to(DEV))
+    torch.cuda.synchronize()
+    assert list(got.shape) == [3, 4, 2, 123457]
+    with torch.no_grad():
+        want = htdemucs_forward(W, cfg, mix)
+    errs = stem_errors(got.cpu(), want)
+    print("short input tf32 per-stem", errs)
+    assert max(errs) < FAST_TOL
