@@ -857,7 +857,8 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   // 256-column tiles for the long-K GEMMs whose epilogue has a compile-time form: one 128x256x8 MMA reads 12 KB of
   // shared memory for the work of two 128x128x8 MMAs (16 KB) -- the tf32 kernel is operand-bandwidth-bound
   static const bool wide_ok = getenv("BD_TC_NO_WIDE") == nullptr;
-  const bool wide = wide_ok && d.math == BD_MATH_TF32 && d.N % 256 == 0 && d.K >= 256 && d.out && !d.convt && !d.oc_split &&
+  static const bool wide_x3 = getenv("BD_TC_NO_WIDE_X3") == nullptr;
+  const bool wide = wide_ok && (d.math == BD_MATH_TF32 || (wide_x3 && d.math == BD_MATH_TF32X3)) && d.N % 256 == 0 && d.K >= 256 && d.out && !d.convt && !d.oc_split &&
                     !d.rowbias && !d.addend && !d.e_stats && (!d.stats_out || d.stat_mod == 1) && bd_epi_vec_ok(d);
   // ... unless the halved tile count quantises badly over the SMs (short M, N = 512: 2.3 waves instead of 4.5)
   auto wave_eff = [&](int tile_n) {
@@ -866,7 +867,8 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   };
   if (wide && wave_eff(256) >= wave_eff(128) - 0.05) {
     g.cpb = d.Cin / 16;
-    rc = launch_tc_persist<16, 256, false>(d, g, items, st);
+    rc = d.math == BD_MATH_TF32X3 ? launch_tc_persist<16, 256, true>(d, g, items, st)
+                                  : launch_tc_persist<16, 256, false>(d, g, items, st);
     *handled = 1;
     return rc;
   }
