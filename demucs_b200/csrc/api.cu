@@ -34,7 +34,7 @@ long long bd_attention_ws_floats(int B, int H, int Tq, int Tk, int math);
 extern "C" {
 
 const char* bd_last_error(void) { return g_err; }
-int bd_version(void) { return 1; }
+int bd_version(void) { return 2; }   // 2: workspace queries, math arguments, conv0 / conv3 entry points
 
 int bd_conv_gemm(const bd_gemm_desc* d, void* stream) {
   if (!d) {
