@@ -176,8 +176,10 @@ class Engine:
             raise _lib.KernelError("demucs_b200 runs on CUDA devices only (there is no CPU path)")
         _lib.lib()  # fail loudly now if the extension is missing
         self.W = PackedWeights(cfg, state, self.device, tc_forms=(mode != "fp32"))
-        self.window = torch.hann_window(cfg.nfft, periodic=True, dtype=torch.float32).to(self.device)
+        # periodic Hann window and twiddles: computed in float64 and rounded once (torch.hann_window in float32 was
+        # seen to come back ~3e-5 off on some runs of the same host, which is visible at the 1e-5 STFT tolerance)
         k = np.arange(cfg.nfft, dtype=np.float64)
+        self.window = torch.from_numpy((0.5 - 0.5 * np.cos(2 * np.pi * k / cfg.nfft)).astype(np.float32)).to(self.device)
         tw = np.stack([np.cos(2 * np.pi * k / cfg.nfft), -np.sin(2 * np.pi * k / cfg.nfft)], axis=1)
         self.twiddle = torch.from_numpy(tw.astype(np.float32)).to(self.device).contiguous()
         self._bufs: tp.Dict[tp.Tuple, tp.Dict[str, torch.Tensor]] = {}
