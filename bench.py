@@ -101,10 +101,8 @@ def ncu_traffic(label: str):
     with open(path) as f:
         table = json.load(f)["kernels"]
     if label.startswith("conv_gemm_tc<"):
-        tbn = label[len("conv_gemm_tc<"):-1]
-        widths = {"128": ("128", "256")}.get(tbn, (tbn,))      # the engine labels every N > 64 layer <128>
-        rows = [r for r in table if r["kernel"].startswith("conv_gemm_tc_persist_kernel<") and
-                r["kernel"].split(",")[1].strip() in widths and r["kernel"].rstrip(">").split(",")[2].strip() == "0"]
+        tbk, tbn = label[len("conv_gemm_tc<"):-1].split(",")     # label = kernel template <TBK,TBN>
+        rows = [r for r in table if r["kernel"].replace(" ", "") == f"conv_gemm_tc_persist_kernel<{tbk},{tbn},0>"]
     else:
         key = {"attention_tc": "attention_tc_kernel<0>"}.get(label, label)
         rows = [r for r in table if r["kernel"].startswith(key)]

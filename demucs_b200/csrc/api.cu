@@ -25,6 +25,7 @@ int bd_check_launch(const char* what) {
 int bd_conv_gemm_simt(const bd_gemm_desc* d, void* stream);
 int bd_conv_gemm_tc(const bd_gemm_desc* d, void* stream, int* handled);
 bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d);
+int bd_conv_gemm_tc_tile(const bd_gemm_desc& d);
 int bd_attention_simt(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
                       int ldk, int ldv, int ldo, void* stream);
 int bd_attention_tc(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,
@@ -50,7 +51,7 @@ int bd_conv_gemm(const bd_gemm_desc* d, void* stream) {
 }
 
 int bd_conv_gemm_arm(const bd_gemm_desc* d) {
-  return (d && (d->math == BD_MATH_TF32 || d->math == BD_MATH_TF32X3) && bd_conv_gemm_tc_eligible(*d)) ? 1 : 0;
+  return (d && (d->math == BD_MATH_TF32 || d->math == BD_MATH_TF32X3)) ? bd_conv_gemm_tc_tile(*d) : 0;
 }
 
 int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk, int ldq,

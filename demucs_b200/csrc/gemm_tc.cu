@@ -836,12 +836,9 @@ bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d) {
   return true;
 }
 
-int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
-  const bd_gemm_desc& d = *dp;
-  *handled = 0;
-  if (!bd_conv_gemm_tc_eligible(d)) return BD_OK;
-  BD_REQUIRE(d.act != BD_ACT_GLU || d.N % 2 == 0, "bd_conv_gemm: GLU needs even N");
-  BD_REQUIRE(d.M % ((long long)d.I0 * d.I1) == 0, "bd_conv_gemm: M not a multiple of I1*I0");
+namespace {
+
+TileGeom tile_geometry(const bd_gemm_desc& d) {
   TileGeom g;
   g.R0 = (d.I0 >= 128 || d.I1 == 1) ? 128 : (pow2_ceil(d.I0) > 128 ? 128 : pow2_ceil(d.I0));
   g.R1 = 128 / g.R0;
@@ -850,22 +847,51 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   g.blocks0 = (d.I0 + g.R0 - 1) / g.R0;
   g.blocks1 = (d.I1 + g.R1 - 1) / g.R1;
   g.stride4 = d.m0 == 4;
-  const int items = d.M / (d.I0 * d.I1);
-  int rc;
-  const int tbn = d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
-  const cudaStream_t st = (cudaStream_t)stream;
-  // 256-column tiles for the long-K GEMMs whose epilogue has a compile-time form: one 128x256x8 MMA reads 12 KB of
-  // shared memory for the work of two 128x128x8 MMAs (16 KB) -- the tf32 kernel is operand-bandwidth-bound
+  g.cpb = 0;
+  return g;
+}
+
+// Tile width of an eligible descriptor.  256-column tiles for the long-K GEMMs whose epilogue has a compile-time
+// form: one 128x256x8 MMA reads 12 KB of shared memory for the work of two 128x128x8 MMAs (16 KB) -- the tf32
+// kernel is operand-bandwidth-bound -- unless the halved tile count quantises badly over the SMs (short M, N = 512:
+// 2.3 waves instead of 4.5).
+int tile_width(const bd_gemm_desc& d, const TileGeom& g) {
   static const bool wide_ok = getenv("BD_TC_NO_WIDE") == nullptr;
   static const bool wide_x3 = getenv("BD_TC_NO_WIDE_X3") == nullptr;
-  const bool wide = wide_ok && (d.math == BD_MATH_TF32 || (wide_x3 && d.math == BD_MATH_TF32X3)) && d.N % 256 == 0 && d.K >= 256 && d.out && !d.convt && !d.oc_split &&
-                    !d.rowbias && !d.addend && !d.e_stats && (!d.stats_out || d.stat_mod == 1) && bd_epi_vec_ok(d);
-  // ... unless the halved tile count quantises badly over the SMs (short M, N = 512: 2.3 waves instead of 4.5)
+  const int items = d.M / (d.I0 * d.I1);
+  const bool wide = wide_ok && (d.math == BD_MATH_TF32 || (wide_x3 && d.math == BD_MATH_TF32X3)) && d.N % 256 == 0 &&
+                    d.K >= 256 && d.out && !d.convt && !d.oc_split && !d.rowbias && !d.addend && !d.e_stats &&
+                    (!d.stats_out || d.stat_mod == 1) && bd_epi_vec_ok(d);
   auto wave_eff = [&](int tile_n) {
     const long long t = (long long)items * g.blocks1 * g.blocks0 * ((d.N + tile_n - 1) / tile_n);
     return (double)t / (double)(((t + 147) / 148) * 148);
   };
-  if (wide && wave_eff(256) >= wave_eff(128) - 0.05) {
+  if (wide && wave_eff(256) >= wave_eff(128) - 0.05) return 256;
+  return d.N <= 16 ? 16 : d.N <= 32 ? 32 : d.N <= 64 ? 64 : 128;
+}
+
+}  // namespace
+
+// 0: the descriptor is not eligible for the tensor-core arm; else 1000 * TBK + TBN of the kernel template it runs
+int bd_conv_gemm_tc_tile(const bd_gemm_desc& d) {
+  if (!bd_conv_gemm_tc_eligible(d) || d.M % ((long long)d.I0 * d.I1) != 0) return 0;
+  const int tbn = tile_width(d, tile_geometry(d));
+  const int tbk = (tbn == 256 || d.math == BD_MATH_TF32X3 || d.Cin % 32 != 0) ? 16 : 32;
+  return 1000 * tbk + tbn;
+}
+
+int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
+  const bd_gemm_desc& d = *dp;
+  *handled = 0;
+  if (!bd_conv_gemm_tc_eligible(d)) return BD_OK;
+  BD_REQUIRE(d.act != BD_ACT_GLU || d.N % 2 == 0, "bd_conv_gemm: GLU needs even N");
+  BD_REQUIRE(d.M % ((long long)d.I0 * d.I1) == 0, "bd_conv_gemm: M not a multiple of I1*I0");
+  TileGeom g = tile_geometry(d);
+  const int items = d.M / (d.I0 * d.I1);
+  int rc;
+  const int tbn = tile_width(d, g);
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (tbn == 256) {
     g.cpb = d.Cin / 16;
     rc = d.math == BD_MATH_TF32X3 ? launch_tc_persist<16, 256, true>(d, g, items, st)
                                   : launch_tc_persist<16, 256, false>(d, g, items, st);

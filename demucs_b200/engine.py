@@ -246,9 +246,11 @@ class Engine:
         nbytes = 4.0 * (rows_in * Cin + N * K + (M * (N if convt else n_out) if out is not None else 0))
         nbytes += 4.0 * M * n_out * ((resid is not None) + (addend is not None))
         arm = "simt"
-        if d.math != _lib.MATH_FP32 and _lib.TEST_HOOK is None:
-            arm = "tc" if _lib.lib().bd_conv_gemm_arm(C.byref(d)) else "simt"
         tile = 128 if N > 64 else 64 if N > 32 else 32 if (N > 16 or act == _lib.ACT_GLU) else 16
+        if d.math != _lib.MATH_FP32 and _lib.TEST_HOOK is None:
+            code = _lib.lib().bd_conv_gemm_arm(C.byref(d))         # 0: CUDA-core arm, else 1000*TBK + TBN
+            if code:
+                arm, tile = "tc", f"{code // 1000},{code % 1000}"
         self._k("bd_conv_gemm", C.byref(d), self._stream(), flops=2.0 * M * N * K, nbytes=nbytes,
                 label=f"conv_gemm_{arm}<{tile}>",
                 detail=f"M={M} N={N} K={K} taps={len(taps)} act={act} a={a_mode} stats={int(stats_out is not None)}")

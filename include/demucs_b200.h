@@ -111,7 +111,8 @@ int bd_istft_ola(const float* spec, const float* norm, const float* window, cons
 
 /* K3/K4/K7: implicit-GEMM convolution / linear layer, see bd_gemm_desc. */
 int bd_conv_gemm(const bd_gemm_desc* desc, void* stream);
-/* Which arm bd_conv_gemm will use for this descriptor: 0 = fp32 CUDA-core, 1 = tcgen05 TF32. */
+/* Which arm bd_conv_gemm will use for this descriptor: 0 = fp32 CUDA-core, else 1000*TBK + TBN of the tcgen05
+ * kernel template (k-block depth 16/32, tile width 16..256). */
 int bd_conv_gemm_arm(const bd_gemm_desc* desc);
 
 /* K5 (GroupNorm(1,C) demucs.py:123, MyGroupNorm transformer.py:258-268): (sum,sumsq) -> (mean, rstd),
