@@ -9,7 +9,7 @@
 
 namespace {
 
-__global__ void finalize_group_stats_kernel(const double* __restrict__ sums, float* __restrict__ out, int slabs,
+__global__ void finalize_group_stats_kernel(double* __restrict__ sums, float* __restrict__ out, int slabs,
                                             double count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= slabs) return;
@@ -18,6 +18,8 @@ __global__ void finalize_group_stats_kernel(const double* __restrict__ sums, flo
   if (var < 0.0) var = 0.0;
   out[2 * i] = (float)mean;
   out[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+  sums[2 * i] = 0.0;        // hand the accumulators back cleared: the next producer adds into them directly
+  sums[2 * i + 1] = 0.0;
 }
 
 // x[m, c] += scale[c] * ( gn(u[m, 2c]) * sigmoid(gn(u[m, 2c+1])) ), gn affine indexed by interleaved column
@@ -164,7 +166,7 @@ __global__ void group_norm_apply_kernel(float* __restrict__ x, const float* __re
 
 extern "C" {
 
-int bd_finalize_group_stats(const double* sums, float* mean_rstd, int slabs, double count, void* stream) {
+int bd_finalize_group_stats(double* sums, float* mean_rstd, int slabs, double count, void* stream) {
   BD_REQUIRE(slabs > 0 && count > 0, "bd_finalize_group_stats: bad sizes");
   finalize_group_stats_kernel<<<bd_cdiv(slabs, 128), 128, 0, (cudaStream_t)stream>>>(sums, mean_rstd, slabs, count);
   return bd_check_launch("finalize_group_stats_kernel");

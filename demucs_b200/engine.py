@@ -207,13 +207,22 @@ class Engine:
         launch, recorded with CUDA events when a profile is being taken."""
         self.launches += kernels          # kernel launches behind this entry point (bench.py's gpu_launches)
         if self._prof is None:
-            _lib.call(name, *args)
+            self._call(name, *args)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.call(name, *args)
+        self._call(name, *args)
         e1.record()
         self._prof.append((label or name, e0, e1, flops, nbytes, detail))
+
+    def _call(self, name: str, *args) -> None:
+        try:
+            _lib.call(name, *args)
+        except Exception:
+            # some workspaces are self-clearing (statistics accumulators, Gram matrices): a forward that dies half-way
+            # would leave them dirty, so drop every cached buffer before the error propagates
+            self._bufs.clear()
+            raise
 
     def _gemm(self, *, M, N, Cin, x, w, out, taps=((0, 0),), I1=1, I0=None, m1=1, m0=1, J1=1, J0=None,
               xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
@@ -269,7 +278,7 @@ class Engine:
         narrow = self.mode == "tf32" and hid == 6 and C_ == 48     # dedicated mma.sync conv3, h stored 8 wide
         hp = 8 if narrow else ((hid + 15) // 16 * 16 if tc else hid)   # tensor-core arm: h is 16-column padded
         h = self._buf(key, f"dconv_h{tag}", M * hp)
-        sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64)
+        sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64, zero=True)   # finalize clears it again
         mr1 = self._buf(key, f"dconv_mr1{tag}", 2 * slabs)
         mr2 = self._buf(key, f"dconv_mr2{tag}", 2 * slabs)
         sfx = "p" if tc else ""
@@ -277,7 +286,6 @@ class Engine:
             p = f"{prefix}.dconv.layers.{dd}"
             dil = 2 ** dd
             # (1) h = conv3_dilated(x) and the GroupNorm statistics of h
-            sums.zero_()
             if narrow:
                 self._k("bd_dconv_conv3", ptr(x), ptr(W[f"{p}.w1"]), ptr(W[f"{p}.b1"]), ptr(h), hp, ptr(sums), M, C_, hid,
                         T * Fr, Fr, dil, self._stream(), flops=2.0 * M * hid * 3 * C_, nbytes=4.0 * M * (C_ + hid),
@@ -294,7 +302,6 @@ class Engine:
             self._k("bd_finalize_group_stats", ptr(sums), ptr(mr1), slabs, float(T * hid), self._stream())
             # (2) statistics of u = conv1x1(gelu(gn(h))) WITHOUT storing u: the expanded [.., 2C] tensor never
             #     touches HBM, both passes recompute it from the 8x narrower h (csrc/dconv.cu)
-            sums.zero_()
             gram = self._buf(key, f"dconv_gram{tag}.{hid}", (slabs + 1) * (hid * hid + hid) + hid + 2, dtype=torch.float64,
                              zero=True)     # zero once: the kernels hand it back cleared
             self._k("bd_dconv_expand_stats", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
@@ -370,9 +377,8 @@ class Engine:
         hbuf = self._buf(key, f"ffn{tag}", M * Hd)
         self._gemm(M=M, N=Hd, Cin=D, x=ln, w=W[f"{p}.linear1.weight"], bias=W[f"{p}.linear1.bias"], out=hbuf,
                    act=_lib.ACT_GELU)
-        sums = self._buf(key, f"no_sums{tag}", 2 * B, torch.float64)
+        sums = self._buf(key, f"no_sums{tag}", 2 * B, torch.float64, zero=True)   # finalize clears it again
         mr = self._buf(key, f"no_mr{tag}", 2 * B)
-        sums.zero_()
         self._gemm(M=M, N=D, Cin=Hd, x=hbuf, w=W[f"{p}.linear2.weight"], bias=W[f"{p}.linear2.bias"], out=x,
                    resid=x, scale=W[f"{p}.gamma_2.scale"], I1=1, I0=T, J0=T, xs=(T * Hd, 0, Hd, 1),
                    os_=(T * D, 0, D), stats_out=sums, stat=(T, 1, 1))

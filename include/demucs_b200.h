@@ -116,8 +116,9 @@ int bd_conv_gemm(const bd_gemm_desc* desc, void* stream);
 int bd_conv_gemm_arm(const bd_gemm_desc* desc);
 
 /* K5 (GroupNorm(1,C) demucs.py:123, MyGroupNorm transformer.py:258-268): (sum,sumsq) -> (mean, rstd),
- * biased variance, eps 1e-5.  count = elements per slab. */
-int bd_finalize_group_stats(const double* sums, float* mean_rstd, int slabs, double count, void* stream);
+ * biased variance, eps 1e-5.  count = elements per slab.  The sums are cleared afterwards, so a buffer that starts
+ * at zero needs no fill between one accumulate -> finalize round and the next. */
+int bd_finalize_group_stats(double* sums, float* mean_rstd, int slabs, double count, void* stream);
 /* DConv tail (demucs.py:141-142,151-153): x[m, c] += scale[c] * GLU(GN(u))[m, c]; u [M, 2C] with
  * interleaved (value, gate) columns; GroupNorm slab of row m =
  * (m / rows_per_item) * slabs_per_item + m % slabs_per_item  (time: 1 slab per item; freq: one per bin). */

@@ -183,6 +183,7 @@ def bd_finalize_group_stats(sums, mean_rstd, slabs, count, stream):
     var = np.maximum(s[:, 1] / count - mean * mean, 0)
     o[:, 0] = mean
     o[:, 1] = 1.0 / np.sqrt(var + 1e-5)
+    s[:] = 0.0          # the accumulators are handed back cleared
 
 
 def bd_dconv_tail(x, u, mr, gamma, beta, scale, M, Cc, rows_per_item, spi, stream):
