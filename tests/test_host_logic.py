@@ -133,3 +133,26 @@ def test_emulated_encoder_conv0(channel_major):
     xn = F.pad((xin - 0.3) * 1.7, (2, 4 * Io + 6 - Jin))
     want = F.gelu(F.conv1d(xn, w, b, stride=4))[..., :Io].reshape(B, I1, cout, Io).permute(0, 1, 3, 2)
     assert rel_l2(out, want) < 1e-5
+
+
+def test_engine_tf32_host_paths_with_48_channels():
+    """The dedicated first-layer / DConv entry points are only taken with the htdemucs channel count (48 -> hid 6):
+    run the engine's host logic in "tf32" mode on a short 48-channel model through the emulated ABI and compare with
+    the oracle (the emulator computes in fp32, so this checks wiring, geometry and workspaces, not rounding)."""
+    from fractions import Fraction
+    from demucs_b200.config import HTDemucsConfig
+    cfg = HTDemucsConfig(sources=["a", "b"], channels=48, dconv_mode=3, bottom_channels=128, t_heads=2, t_layers=1,
+                         segment=Fraction(1, 2))
+    cfg.validate()
+    W = init_weights(cfg, 5, layer_scale=0.5)
+    mix = synth_mix(2, cfg.segment_length, 12)
+    with torch.no_grad():
+        want = htdemucs_forward(W, cfg, mix)
+    import abi_emulator as E
+    with emulated_abi():
+        E.CALLS.clear()
+        eng = Engine(cfg, W, "cpu", mode="tf32")
+        got = eng.forward(mix)
+        calls = set(E.CALLS)
+    assert {"bd_encoder_conv0", "bd_dconv_conv3", "bd_dconv_expand_stats", "bd_dconv_expand_update"} <= calls
+    assert rel_l2(got, want) < 1e-5
