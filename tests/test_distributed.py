@@ -51,6 +51,7 @@ def _single(kwargs, length):
 @pytest.mark.parametrize("kwargs,length", [
     (dict(shifts=0, overlap=0.25), 190000),       # 4 segments -> 2 + 2, one halo segment
     (dict(shifts=1, overlap=0.6), 120000),        # heavy overlap: 2 halo segments, shifted window, RNG in step
+    (dict(shifts=0, overlap=0.25), 60000),        # one segment on two ranks: rank 1 owns nothing (empty gather piece)
 ])
 def test_sharded_apply_matches_single_process(kwargs, length):
     ctx = mp.get_context("spawn")
