@@ -13,7 +13,7 @@ import typing as tp
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdemucs_b200.so")
-SOURCES = ["api.cu", "spectral.cu", "gemm_simt.cu", "gemm_tc.cu", "norm.cu", "dconv.cu", "attention.cu", "attention_tc.cu",
+SOURCES = ["api.cu", "spectral.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_b16x3.cu", "gemm_tc_b16.cu", "norm.cu", "dconv.cu", "attention.cu", "attention_tc.cu", "attention_b16.cu",
            "ola.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 BD_MAX_TAPS = 9
 A_NONE, A_GN_GELU, A_ITEM_AFFINE = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_GLU = 0, 1, 2
-MATH_FP32, MATH_TF32, MATH_TF32X3 = 0, 1, 2
+MATH_FP32, MATH_TF32, MATH_TF32X3, MATH_BF16X3, MATH_BF16 = 0, 1, 2, 3, 4
 
 
 class KernelError(RuntimeError):
@@ -46,7 +46,7 @@ class GemmDesc(C.Structure):
         ("out", C.c_void_p), ("os_b", C.c_longlong), ("os_1", C.c_longlong), ("os_0", C.c_longlong),
         ("convt", C.c_int), ("O0", C.c_int), ("oc_split", C.c_int), ("oc_stride", C.c_longlong),
         ("stats_out", C.c_void_p), ("stat_div", C.c_int), ("stat_mul", C.c_int), ("stat_mod", C.c_int),
-        ("math", C.c_int),
+        ("math", C.c_int), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p),
     ]
 
 
@@ -80,34 +80,62 @@ _lib: tp.Optional[C.CDLL] = None
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
-    """Compile csrc/*.cu into libdemucs_b200.so for sm_100a (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"),
-                   os.path.join(os.path.dirname(HERE), "include", "demucs_b200.h")]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    """Compile csrc/*.cu into libdemucs_b200.so for sm_100a (cross-compiles without a GPU).
+
+    Every source becomes its own object file (compiled in parallel, cached under csrc/.obj by the content
+    hash of the source, the shared headers and the flags), then one link step."""
     import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    headers = [os.path.join(os.path.dirname(HERE), "include", "demucs_b200.h")]
+    headers += sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     flags += os.environ.get("BD_NVCC_DEFS", "").split()     # experiment knobs, e.g. -DBD_TC_PIPE_BYTES=196608
-    digest = hashlib.sha256(" ".join(flags).encode())
-    for dep in sorted(set(deps)):
+    base = hashlib.sha256(" ".join(flags).encode())
+    for dep in headers:
         with open(dep, "rb") as f:
-            digest.update(f.read())
+            base.update(f.read())
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objdir = os.path.join(CSRC, ".obj")
+    os.makedirs(objdir, exist_ok=True)
+    total = base.copy()
+    jobs = []
+    for src in srcs:
+        d = base.copy()
+        with open(src, "rb") as f:
+            data = f.read()
+        d.update(data)
+        total.update(data)
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        jobs.append((src, obj, d.hexdigest()))
     stamp_path = LIB_PATH + ".stamp"
-    stamp = digest.hexdigest()
+    stamp = total.hexdigest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_path):
         with open(stamp_path) as f:
             if f.read().strip() == stamp:       # content hash: file times do not survive a snapshot
                 return LIB_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + flags + ["-shared", "-o", LIB_PATH] + srcs
+
+    def compile_one(job):
+        src, obj, digest = job
+        if not force and os.path.exists(obj) and os.path.exists(obj + ".stamp"):
+            with open(obj + ".stamp") as f:
+                if f.read().strip() == digest:
+                    return ""
+        cmd = [nvcc] + flags + (["-Xptxas=-v"] if verbose else []) + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise KernelError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
+        with open(obj + ".stamp", "w") as f:
+            f.write(digest)
+        return res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+        logs = list(pool.map(compile_one, jobs))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        print("\n".join(logs))
+    res = subprocess.run([nvcc] + flags + ["-shared", "-o", LIB_PATH] + [j[1] for j in jobs], capture_output=True, text=True)
     if res.returncode != 0:
-        raise KernelError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+        raise KernelError(f"link failed:\n{res.stdout}\n{res.stderr}")
     with open(stamp_path, "w") as f:
         f.write(stamp)
     return LIB_PATH

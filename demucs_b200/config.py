@@ -23,7 +23,7 @@ class UnsupportedConfig(ValueError):
 _PINNED = {
     "wiener_iters": 0, "end_iters": 0, "wiener_residual": False, "cac": True,
     "rewrite": True, "multi_freqs": None, "kernel_size": 8, "stride": 4,
-    "context": 1, "context_enc": 0, "t_emb": "sin", "t_dropout": 0.0,
+    "context": 1, "context_enc": 0, "t_emb": "sin",
     "t_norm_in": True, "t_norm_in_group": False, "t_group_norm": False,
     "t_norm_first": True, "t_norm_out": True, "t_layer_scale": True,
     "t_gelu": True, "t_sin_random_shift": 0, "t_sparse_self_attn": False,
@@ -36,6 +36,7 @@ _IGNORED = {
     "t_weight_decay", "t_lr", "t_cape_mean_normalize", "t_cape_augment",
     "t_cape_glob_loc_scale", "t_mask_type", "t_mask_random_seed", "t_sparse_attn_window",
     "t_global_window", "t_sparsity", "t_auto_sparsity", "rescale", "dconv_attn", "dconv_lstm",
+    "t_dropout",          # inert in eval mode; the released htdemucs models record 0.02 (grids/mmi.py:22)
 }
 
 

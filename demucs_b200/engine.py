@@ -26,7 +26,15 @@ from ._lib import GemmDesc, call, ptr
 from .config import HTDemucsConfig
 from .weights import check_state_dict
 
-MODES = ("fp32", "tf32", "tf32x3")
+# Precision modes.  "strict" is the default of the drop-in: fp32 activations in HBM, every
+# contraction on the tensor cores with error-compensated operands (bf16 hi/lo split, three products: 16 mantissa
+# bits per operand) -- per-stem rel-L2 <= 1e-4 against the fp32 reference.  "bf16" is the reduced-precision mode
+# (single bf16 product, <= 1e-2).  "tf32x3" / "tf32" are the kind::tf32 forms of the same two ideas, "fp32" runs the
+# contractions on CUDA cores.
+MODES = ("fp32", "tf32", "tf32x3", "strict", "bf16")
+_GEMM_MATH = {"fp32": _lib.MATH_FP32, "tf32": _lib.MATH_TF32, "tf32x3": _lib.MATH_TF32X3, "strict": _lib.MATH_BF16X3,
+              "bf16": _lib.MATH_BF16}
+_ATTN_MATH = dict(_GEMM_MATH)
 
 
 def _interleave_glu(w: torch.Tensor) -> torch.Tensor:
@@ -182,6 +190,8 @@ class Engine:
         self.window = torch.from_numpy((0.5 - 0.5 * np.cos(2 * np.pi * k / cfg.nfft)).astype(np.float32)).to(self.device)
         tw = np.stack([np.cos(2 * np.pi * k / cfg.nfft), -np.sin(2 * np.pi * k / cfg.nfft)], axis=1)
         self.twiddle = torch.from_numpy(tw.astype(np.float32)).to(self.device).contiguous()
+        self.single_pass = mode in ("tf32", "bf16")      # reduced-precision modes: single-pass mma.sync thin-layer kernels
+        self._w16_cache: tp.Dict[tp.Tuple, tp.Tuple[torch.Tensor, torch.Tensor]] = {}
         self._bufs: tp.Dict[tp.Tuple, tp.Dict[str, torch.Tensor]] = {}
         self._pos: tp.Dict[tp.Tuple, torch.Tensor] = {}
         self.launches = 0
@@ -224,6 +234,19 @@ class Engine:
             self._bufs.clear()
             raise
 
+    def _w16(self, w: torch.Tensor) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+        """bf16 hi / lo planes of a packed weight matrix (or of a row slice of one): hi = bf16(w), lo = bf16(w - hi).
+        Made once per weight, on the device; the tcgen05 bf16 arms read them by TMA."""
+        key = (w.data_ptr(), tuple(w.shape))
+        got = self._w16_cache.get(key)
+        if got is None:
+            w = w.contiguous()
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            got = (hi.contiguous(), lo.contiguous(), w)       # keep `w` alive: the key is its address
+            self._w16_cache[key] = got
+        return got[0], got[1]
+
     def _gemm(self, *, M, N, Cin, x, w, out, taps=((0, 0),), I1=1, I0=None, m1=1, m0=1, J1=1, J0=None,
               xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
               a_stats_stride=0, a_gamma=None, a_beta=None, act=_lib.ACT_NONE, rowbias=None, rowbias_period=0,
@@ -248,8 +271,10 @@ class Engine:
         d.oc_split, d.oc_stride = oc_split, oc_stride
         d.stats_out = ptr(stats_out)
         d.stat_div, d.stat_mul, d.stat_mod = stat
-        d.math = _lib.MATH_FP32 if (self.mode == "fp32" or not tc) else \
-            (_lib.MATH_TF32 if self.mode == "tf32" else _lib.MATH_TF32X3)
+        d.math = _lib.MATH_FP32 if not tc else _GEMM_MATH[self.mode]
+        if d.math in (_lib.MATH_BF16X3, _lib.MATH_BF16) and Cin % 16 == 0 and _lib.TEST_HOOK is None:
+            hi, lo = self._w16(w)
+            d.w16_hi, d.w16_lo = ptr(hi), ptr(lo)
         K = len(taps) * Cin
         rows_in = (M // (I1 * I0)) * d.J1 * d.J0          # input positions (each read once, algorithmically)
         nbytes = 4.0 * (rows_in * Cin + N * K + (M * (N if convt else n_out) if out is not None else 0))
@@ -275,7 +300,7 @@ class Engine:
         slabs = B * Fr
         stat = (T * Fr, Fr, Fr)                      # slab(m) = b*Fr + fr
         tc = self.mode != "fp32"
-        narrow = self.mode == "tf32" and hid == 6 and C_ == 48     # dedicated mma.sync conv3, h stored 8 wide
+        narrow = self.single_pass and hid == 6 and C_ == 48     # dedicated mma.sync conv3, h stored 8 wide
         hp = 8 if narrow else ((hid + 15) // 16 * 16 if tc else hid)   # tensor-core arm: h is 16-column padded
         h = self._buf(key, f"dconv_h{tag}", M * hp)
         sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64, zero=True)   # finalize clears it again
@@ -313,7 +338,7 @@ class Engine:
             #     "tf32" mode, exact FFMA otherwise).  The widest layers (hid 48; in "tf32x3" also hid 24) are a real
             #     GEMM and go through the tcgen05 kernel instead: activate h once, then GroupNorm / GLU /
             #     LayerScale / residual in the GEMM epilogue.
-            if tc and hid >= (48 if self.mode == "tf32" else 24):
+            if tc and hid >= (48 if self.single_pass else 24):
                 self._k("bd_gn_gelu_apply", ptr(h), ptr(mr1), ptr(W[f"{p}.g1p"]), ptr(W[f"{p}.be1p"]), M, hp, T * Fr, Fr,
                         self._stream(), nbytes=8.0 * M * hp, label="bd_gn_gelu_apply")
                 self._gemm(M=M, N=2 * C_, Cin=hp, x=h, w=W[f"{p}.w2p"], bias=W[f"{p}.b2"], e_stats=mr2,
@@ -322,7 +347,8 @@ class Engine:
                 continue
             self._k("bd_dconv_expand_update", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
                     ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(mr2), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
-                    ptr(W[f"{p}.scale"]), ptr(x), M, C_, T * Fr, Fr, self._math(), self._stream(),
+                    ptr(W[f"{p}.scale"]), ptr(x), M, C_, T * Fr, Fr,
+                    _lib.MATH_TF32 if self.single_pass else _lib.MATH_FP32, self._stream(),
                     nbytes=4.0 * M * (hid + 2 * C_), flops=4.0 * M * hid * C_, label="dconv_expand_update",
                     detail=f"M={M} C={C_} hid={hid}")
 
@@ -334,7 +360,8 @@ class Engine:
         nws = _lib.call_value("bd_attention_workspace", B, H, Tq, Tk, self._math())
         ws = self._buf(key, f"att_ws{tag}", nws) if nws else None
         label = "attention_simt" if self.mode == "fp32" else "attention_tc"
-        nk = {"fp32": 1, "tf32": 2, "tf32x3": 4}[self.mode]     # + V transpose (+ Q / K hi-lo splits)
+        # kernels behind the entry point: + V transpose (+ Q / K splits) / the three bf16 conversions
+        nk = {_lib.MATH_FP32: 1, _lib.MATH_TF32: 2, _lib.MATH_TF32X3: 4, _lib.MATH_BF16X3: 4, _lib.MATH_BF16: 4}[self._math()]
         if kv_src is None:  # self attention: one packed projection
             qkv = self._buf(key, f"qkv{tag}", B * Tq * 3 * D)
             self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv)
@@ -354,7 +381,7 @@ class Engine:
     def _math(self) -> int:
         """Arithmetic of the attention core: tcgen05 in both tensor-core modes (three-pass hi/lo products in
         "tf32x3"), CUDA cores in "fp32"."""
-        return {"tf32": _lib.MATH_TF32, "tf32x3": _lib.MATH_TF32X3}.get(self.mode, _lib.MATH_FP32)
+        return _ATTN_MATH[self.mode]
 
     def _ln(self, x, y, p: str, M: int, pos=None, period=0):
         D = self.cfg.transformer_dim
@@ -388,8 +415,20 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, mix: torch.Tensor, taps: tp.Optional[dict] = None) -> torch.Tensor:
-        """mix [B, 2, L <= segment_length] (fp32, on self.device) -> [B, S, 2, L]."""
+    def forward(self, mix: torch.Tensor, taps: tp.Optional[dict] = None, out: tp.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """mix [B, 2, L <= segment_length] (fp32, on self.device) -> [B, S, 2, L] (written into ``out`` when given)."""
+        # kernels launch on the CURRENT device: make that the engine's device whatever the caller's is; and any
+        # failure -- not only a kernel error -- may leave the self-clearing statistics workspaces dirty
+        try:
+            if self.device.type == "cuda":
+                with torch.cuda.device(self.device):
+                    return self._forward(mix, taps, out)
+            return self._forward(mix, taps, out)
+        except BaseException:
+            self._bufs.clear()
+            raise
+
+    def _forward(self, mix: torch.Tensor, taps: tp.Optional[dict], out_buf: tp.Optional[torch.Tensor]) -> torch.Tensor:
         cfg, W = self.cfg, self.W
         if mix.dim() != 3 or mix.shape[1] != cfg.audio_channels:
             raise ValueError(f"expected mix of shape [B, {cfg.audio_channels}, L], got {tuple(mix.shape)}")
@@ -446,7 +485,7 @@ class Engine:
             y = self._buf(key, "y_t", B * Tout * Cc)
             first = i == 0
             Tin_p = Tin if first else tp(Tin)
-            conv0 = first and self.mode == "tf32" and Cc == 48 and A == 2     # dedicated mma.sync first-layer kernel
+            conv0 = first and self.single_pass and Cc == 48 and A == 2     # dedicated mma.sync first-layer kernel
             if conv0:
                 self._k("bd_encoder_conv0", ptr(xt), 1, norm.data_ptr() + 16, 8, ptr(W[f"tencoder.{i}.conv.w"]),
                         ptr(W[f"tencoder.{i}.conv.b"]), ptr(y), B, 1, Tout, L, A, Cc, self._stream(),
@@ -613,7 +652,13 @@ class Engine:
             xtd = nxt
 
         # ---- K2: de-normalise, iSTFT, overlap-add in shared memory, crop, add the time branch ------------
-        out = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
+        if out_buf is not None:
+            if out_buf.numel() != B * S * A * L0 or out_buf.dtype != torch.float32 or out_buf.device != self.device \
+                    or not out_buf.is_contiguous():
+                raise ValueError("out must be a contiguous float32 tensor of B*S*C*L elements on the engine's device")
+            out = out_buf.view(B, S, A, L0)
+        else:
+            out = torch.empty(B, S, A, L0, dtype=torch.float32, device=self.device)
         self._k("bd_istft_ola", ptr(xd), ptr(norm), ptr(self.window), ptr(self.twiddle), ptr(xtd), ptr(out),
                 B, S, T, tp(L), L0, st, nbytes=4.0 * B * S * (T * 2048 * 4 + 2 * L + 2 * L0),
                 flops=2.5 * 4096 * 12 * 2 * S * B * T)

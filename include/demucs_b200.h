@@ -29,8 +29,11 @@ enum { BD_A_NONE = 0, BD_A_GN_GELU = 1, BD_A_ITEM_AFFINE = 2 };
 enum { BD_ACT_NONE = 0, BD_ACT_GELU = 1, BD_ACT_GLU = 2 };
 /* Arithmetic of the contraction. */
 /* FP32: CUDA-core FFMA.  TF32: tcgen05 kind::tf32, single pass.  TF32X3: tcgen05, operands split into
- * hi + lo TF32 parts in shared memory, hi*hi + lo*hi + hi*lo (fp32-class accuracy). */
-enum { BD_MATH_FP32 = 0, BD_MATH_TF32 = 1, BD_MATH_TF32X3 = 2 };
+ * hi + lo TF32 parts in shared memory, hi*hi + lo*hi + hi*lo (fp32-class accuracy).
+ * BF16X3: tcgen05 kind::f16, fp32 activations split into bf16 hi + lo in shared memory, weights pre-split
+ * (w16_hi / w16_lo), hi*hi + hi*lo + lo*hi: 16 mantissa bits per operand, ~4e-6 per layer -- the arithmetic of the
+ * default mode (per-stem rel-L2 <= 1e-4).  BF16: single bf16 product (the reduced-precision mode, <= 1e-2). */
+enum { BD_MATH_FP32 = 0, BD_MATH_TF32 = 1, BD_MATH_TF32X3 = 2, BD_MATH_BF16X3 = 3, BD_MATH_BF16 = 4 };
 
 /* One convolution / linear layer expressed as an implicit GEMM
  *   out[m, n] = epilogue( sum_{tap, ci} A(m, tap, ci) * w[n, tap*Cin + ci] + bias[n] )
@@ -86,6 +89,8 @@ typedef struct bd_gemm_desc {
    * frequency branch [B,T,F,C]: one slab per (b, fr): stat_div = T*F, stat_mul = stat_mod = F. */
   int stat_div, stat_mul, stat_mod;
   int math;            /* BD_MATH_* */
+  const void* w16_hi;  /* BD_MATH_BF16X3 / BD_MATH_BF16: bf16 [N, K] = bf16_rn(w) */
+  const void* w16_lo;  /* BD_MATH_BF16X3: bf16 [N, K] = bf16_rn(w - w16_hi) */
 } bd_gemm_desc;
 
 const char* bd_last_error(void);

@@ -41,7 +41,8 @@ SHAPES = [(2, 8, 2688, 2688), (2, 8, 1344, 1344), (1, 8, 2688, 1344), (1, 8, 134
 
 @pytest.mark.parametrize("B,H,Tq,Tk", SHAPES)
 @pytest.mark.parametrize("math_mode,tol", [(_lib.MATH_FP32, 3e-6), (_lib.MATH_TF32, 2e-3),
-                                           (_lib.MATH_TF32X3, 3e-5)])
+                                           (_lib.MATH_TF32X3, 3e-5), (_lib.MATH_BF16X3, 3e-5),
+                                           (_lib.MATH_BF16, 8e-3)])
 def test_attention(B, H, Tq, Tk, math_mode, tol):
     out, want = run(B, H, Tq, Tk, math_mode)
     assert not torch.isnan(out).any()

@@ -38,6 +38,10 @@ def run_plain(M, N, K, math_mode, bias=True, act=_lib.ACT_NONE, resid=False, sta
     d.stats_out = ptr(sums) if stats_rows else None
     d.stat_div, d.stat_mul, d.stat_mod = (stats_rows or M), 1, 1
     d.math = math_mode
+    if math_mode in (_lib.MATH_BF16X3, _lib.MATH_BF16):     # pre-split bf16 weight planes (engine.Engine._w16)
+        w_hi = w.to(torch.bfloat16)
+        w_lo = (w - w_hi.float()).to(torch.bfloat16)
+        d.w16_hi, d.w16_lo = ptr(w_hi), ptr(w_lo)
     _lib.call("bd_conv_gemm", C.byref(d), 0)
     torch.cuda.synchronize()
     want = x.double() @ w.double().t()
@@ -53,11 +57,15 @@ def run_plain(M, N, K, math_mode, bias=True, act=_lib.ACT_NONE, resid=False, sta
 
 
 SHAPES = [(2688, 512, 512), (1344 * 3, 1536, 512), (1000, 2048, 512), (777, 512, 2048), (4096, 96, 96),
-          (128, 64, 32), (5000, 384, 100)]
+          (128, 64, 32), (5000, 384, 100), (3000, 96, 48), (2000, 16, 144), (1500, 48, 1152)]
+
+
+MATHS = [(_lib.MATH_FP32, 3e-6), (_lib.MATH_TF32, 1.5e-3), (_lib.MATH_TF32X3, 2e-5), (_lib.MATH_BF16X3, 2e-5),
+         (_lib.MATH_BF16, 6e-3)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
-@pytest.mark.parametrize("math_mode,tol", [(_lib.MATH_FP32, 2e-6), (_lib.MATH_TF32, 1.5e-3), (_lib.MATH_TF32X3, 2e-5)])
+@pytest.mark.parametrize("math_mode,tol", MATHS)
 def test_plain_gemm(M, N, K, math_mode, tol):
     out, want, _, _ = run_plain(M, N, K, math_mode)
     assert not torch.isnan(out).any()
@@ -66,7 +74,7 @@ def test_plain_gemm(M, N, K, math_mode, tol):
     assert e < tol
 
 
-@pytest.mark.parametrize("math_mode,tol", [(_lib.MATH_FP32, 3e-6), (_lib.MATH_TF32, 1.5e-3), (_lib.MATH_TF32X3, 2e-5)])
+@pytest.mark.parametrize("math_mode,tol", MATHS)
 def test_fused_epilogues(math_mode, tol):
     out, want, _, _ = run_plain(2688, 2048, 512, math_mode, act=_lib.ACT_GELU)
     assert rel_l2(out.cpu(), want.cpu()) < tol
@@ -89,6 +97,10 @@ def test_tf32_arm_really_ran():
     b, _, _, _ = run_plain(2688, 512, 512, _lib.MATH_TF32)
     e = rel_l2(b.cpu(), a.cpu())
     assert 1e-5 < e < 1.5e-3
+    c, _, _, _ = run_plain(2688, 512, 512, _lib.MATH_BF16)
+    assert 2e-4 < rel_l2(c.cpu(), a.cpu()) < 6e-3
+    d_, _, _, _ = run_plain(2688, 512, 512, _lib.MATH_BF16X3)
+    assert 1e-7 < rel_l2(d_.cpu(), a.cpu()) < 2e-5
 
 
 @pytest.mark.parametrize("Fr,dil", [(1, 1), (1, 2), (8, 1), (32, 2)])

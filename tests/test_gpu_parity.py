@@ -276,14 +276,16 @@ def test_forward_blocks_small_tf32_mode():
     assert max(stem_errors(got.cpu(), want)) < FAST_TOL
 
 
+@pytest.mark.parametrize("mode", ["strict", "tf32x3"])
 @pytest.mark.parametrize("name", ["htdemucs_default.npz", "htdemucs_ls05.npz"])
-def test_forward_htdemucs_tf32x3_mode(name):
-    """Error-compensated tensor-core mode (hi*hi + lo*hi + hi*lo on tcgen05, fp32 softmax path): the
-    north_star's fp32/TF32 bound, per-stem relative L2 <= 1e-4, on both weight fixtures."""
+def test_forward_htdemucs_strict_modes(name, mode):
+    """Error-compensated tensor-core modes -- "strict" (the default: bf16 hi/lo operand split, three kind::f16
+    products) and "tf32x3" (the same with tf32 parts) -- against the reference golden vectors: the north_star's
+    fp32/TF32 bound, per-stem relative L2 <= 1e-4, on both weight fixtures, every block tap included."""
     g = golden(name)
     cfg = htdemucs_config()
     W, mix = forward_fixture_inputs(g, cfg)
-    eng = Engine(cfg, W, DEV, mode="tf32x3")
+    eng = Engine(cfg, W, DEV, mode=mode)
     taps = {}
     got = eng.forward(mix.to(DEV), taps)
     torch.cuda.synchronize()
@@ -292,7 +294,7 @@ def test_forward_htdemucs_tf32x3_mode(name):
         if key.startswith("tap."):
             errs[key[4:]] = rel_l2(strided(taps[key[4:]].contiguous(), int(g["tap_stride"])), g[key])
     e_out = rel_l2(strided(got, int(g["stride"])), g["out"])
-    print(name, "tf32x3 out rel-L2", e_out, "worst tap", max(errs.items(), key=lambda kv: kv[1]))
+    print(name, mode, "out rel-L2", e_out, "worst tap", max(errs.items(), key=lambda kv: kv[1]))
     assert max(errs.values()) < 1e-4
     with torch.no_grad():
         want = htdemucs_forward(W, cfg, mix)
