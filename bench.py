@@ -5,14 +5,17 @@
     python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU
 
 Workload (BASELINE.json configs[2]): htdemucs (random-init, 4 stems, 41.98 M parameters), one
-synthetic stereo 44.1 kHz track of 64 x 7.8 s segments PER GPU (overlap 0.25, shifts=0), run
-through ``apply_model``: segments are batched through the kernel engine, overlap-added on the
-device, and -- for N > 1 -- sharded in contiguous blocks across ranks with a halo exchange and a
-final all-reduce of the stems (weak scaling: the track grows with N).  A "step" is one
-``apply_model`` pass over the whole track.
+synthetic stereo 44.1 kHz track of 64 x 7.8 s segments (overlap 0.25, shifts=0) run through
+``apply_model``: segments are batched through the kernel engine, overlap-added on the device, and --
+for N > 1 -- sharded 64/N per rank in contiguous blocks (strong scaling) with an exchange of the
+overlap slabs between neighbours; every rank hands the samples it produced to the host.  A "step" is
+one ``apply_model`` pass over the whole track.  ``weak`` (N > 1) is the same call on a track of 64
+segments PER GPU.
 
 Prints ONE JSON line (rank 0).  ``value`` = track seconds / device time with the track resident
-in HBM; ``e2e`` = the same through the public API from pinned host memory and back.
+in HBM; ``e2e`` = the same through the public API from pinned host memory and back.  The default
+arithmetic ("strict") is the one that meets the north_star's fp32/TF32 tolerance (per-stem rel-L2
+<= 1e-4); ``parity`` holds the measured figure of the run.
 """
 from __future__ import annotations
 
@@ -27,11 +30,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SEGMENTS_PER_GPU = 64
+SEGMENTS = 64               # BASELINE configs[2]
+CPU_SAMPLE_SEGMENTS = 8     # bounded sample of the same track for the CPU arms (about 47 s of audio)
 SEG_LEN = 343980            # int(39/5 * 44100)
 STRIDE = 257985             # int(0.75 * SEG_LEN)
 SR = 44100
-STRICT_MODE = "tf32x3"
 METRIC = "htdemucs audio-seconds separated per second"
 UNIT = "audio-s/s"
 
@@ -43,9 +46,9 @@ def synth_track(length: int, seed: int = 1234):
 
 
 def workload_config(n_gpus: int, mode: str, batch: int) -> dict:
-    return {"workload": f"htdemucs 4-stem random-init, one track of {SEGMENTS_PER_GPU}x7.8s segments per GPU "
-                        f"(BASELINE configs[2]), apply_model overlap=0.25 shifts=0",
-            "segments_per_gpu": SEGMENTS_PER_GPU, "track_seconds": n_gpus * SEGMENTS_PER_GPU * STRIDE / SR,
+    return {"workload": f"htdemucs 4-stem random-init, one track of {SEGMENTS}x7.8s segments (BASELINE configs[2]), "
+                        f"apply_model overlap=0.25 shifts=0, segments sharded {SEGMENTS}/N per GPU",
+            "segments": SEGMENTS, "track_seconds": SEGMENTS * STRIDE / SR,
             "forward_batch": batch, "mode": mode, "parallelism": f"segments sharded x{n_gpus}",
             "l2": "inputs larger than L2 (132 MB track, multi-GB activations per step)"}
 
@@ -91,20 +94,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic(label: str):
+def ncu_traffic(label: str, mode: str):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) and tensor-pipe activity of the kernels
-    behind a profile label, from the committed ncu pass over one 16-segment forward
-    (profiles/r01_ncu_forward_b16_tf32.json, made by tools/ncu_forward_table.py).  None when absent."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_forward_b16_tf32.json")
+    behind a profile label, from the committed ncu pass over one 16-segment forward in this mode
+    (profiles/r02_ncu_forward_b16_<mode>.json, made by tools/ncu_forward_table.py).  None when absent."""
+    path = os.path.join(ROOT, "profiles", f"r02_ncu_forward_b16_{mode}.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
         table = json.load(f)["kernels"]
     if label.startswith("conv_gemm_tc<"):
         tbk, tbn = label[len("conv_gemm_tc<"):-1].split(",")     # label = kernel template <TBK,TBN>
-        rows = [r for r in table if r["kernel"].replace(" ", "") == f"conv_gemm_tc_persist_kernel<{tbk},{tbn},0>"]
+        rows = [r for r in table if r["kernel"].replace(" ", "").startswith(f"conv_gemm_tc_persist_kernel<{tbk},{tbn},")]
     else:
-        key = {"attention_tc": "attention_tc_kernel<0>"}.get(label, label)
+        key = {"attention_tc": "attention_"}.get(label, label)
         rows = [r for r in table if r["kernel"].startswith(key)]
     if not rows:
         return None
@@ -112,7 +115,7 @@ def ncu_traffic(label: str):
     ms = sum(r["ms"] for r in rows)
     return {"bytes_per_launch": sum(r["dram_mb"] for r in rows) * 1e6 / n, "launches": n,
             "tensor_pipe_active": sum(r["tensor_pipe_active"] * r["ms"] for r in rows) / ms,
-            "source": "profiles/r01_ncu_forward_b16_tf32.json"}
+            "source": os.path.relpath(path, ROOT)}
 
 
 def measured_peaks() -> dict:
@@ -135,7 +138,7 @@ def cpu_apply_seconds(length: int, reps: int, threads: int, want_output: bool = 
     torch.set_num_threads(threads)
     cfg = htdemucs_config()
     W = init_weights(cfg, 0)
-    mix = synth_track(length)
+    mix = synth_track(SEGMENTS * STRIDE)[..., :length].contiguous()     # a prefix of the GPU arm's own track
     if refload.available():
         ref = refload.load()
         model = refload.build_reference_model(cfg, W)
@@ -161,20 +164,22 @@ def cpu_apply_seconds(length: int, reps: int, threads: int, want_output: bool = 
 
 
 def reference_arm(args) -> None:
-    """--impl reference: the reference's CPU implementation of the path on this host's cores."""
+    """--impl reference: the reference's CPU implementation of the path on this host's cores, on a bounded sample
+    (the first CPU_SAMPLE_SEGMENTS segments) of the same 64-segment track the GPU arm separates."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    length = 10 * SR                                     # BASELINE configs[0]: 10 s clip, 2 segments
+    length = CPU_SAMPLE_SEGMENTS * STRIDE
     times, kind = cpu_apply_seconds(length, args.warmup + args.steps, threads)
     timed = times[args.warmup:]
     sec = sum(timed) / len(timed)
     value = (length / SR) / sec
-    sample = f"{len(timed)} x apply_model on a 10 s clip (2 segments), {threads} threads, torch CPU fp32"
+    sample = (f"{len(timed)} x apply_model on the first {CPU_SAMPLE_SEGMENTS} segments ({length / SR:.1f} s) of the bench "
+              f"track, {threads} threads, torch CPU fp32")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus, "cpu-fp32", 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,11 +188,17 @@ def reference_arm(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+DTYPE = {"strict": "f32 (bf16 hi/lo split operands, 3 tcgen05 products, fp32 accumulate)",
+         "tf32x3": "f32 (tf32 hi/lo split operands, 3 tcgen05 products, fp32 accumulate)",
+         "tf32": "tf32", "bf16": "bf16", "fp32": "f32"}
+TOLERANCE = {"strict": 1e-4, "tf32x3": 1e-4, "fp32": 1e-4, "bf16": 1e-2, "tf32": None}
+
+
 def gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
     import demucs_b200 as D
-    from demucs_b200 import _lib, perf
+    from demucs_b200 import perf
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,16 +212,12 @@ def gpu_arm(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         from demucs_b200.distributed import Shard
-        shard = Shard()
+        # the stems leave each GPU for the host from the rank that made them: nothing is replicated over NVLink
+        shard = Shard(gather="none")
 
     model = D.htdemucs(mode=args.mode).to(dev)
     eng = model.engine()
-    # the error-compensated arithmetic (3xTF32: per-stem rel-L2 <= 1e-4, north_star's fp32/TF32 tolerance) is timed
-    # beside the headline mode (single-pass TF32: <= 1e-2, north_star's reduced-precision tolerance)
-    strict_model = None
-    if args.mode != STRICT_MODE and not args.no_strict:
-        strict_model = D.htdemucs(mode=STRICT_MODE).to(dev)
-    nseg = SEGMENTS_PER_GPU * world
+    nseg = SEGMENTS                      # BASELINE configs[2]: 64 segments in all, 64/N per GPU (strong scaling)
     length = nseg * STRIDE
     host_mix = synth_track(length).pin_memory()
     dev_mix = host_mix.to(dev)
@@ -224,38 +231,16 @@ def gpu_arm(args) -> None:
     def step_device():
         return D.apply_model(model, dev_mix, device=dev, **kw)
 
-    def step_strict():
-        return D.apply_model(strict_model, dev_mix, device=dev, **kw)
-
-    # End-to-end step: host -> device copy of the input this rank consumes, apply_model, device -> host read of
-    # the sample range this rank produced (N = 1: the whole track both ways).  Over all ranks the reads cover the
-    # result exactly once; every rank still holds the complete result on its device after the gather.
-    if shard is None:
-        in_lo, in_hi, out_lo, out_hi = 0, length, 0, length
-    else:
-        lo_seg, hi_seg = shard.block(nseg)
-        first = max(0, lo_seg - shard.halo(SEG_LEN, STRIDE))
-        in_lo, in_hi = first * STRIDE, min(length, (hi_seg - 1) * STRIDE + SEG_LEN)
-        out_lo, out_hi = lo_seg * STRIDE, (length if hi_seg == nseg else hi_seg * STRIDE)
-    host_out = torch.empty(1, 4, 2, out_hi - out_lo).pin_memory()
-    e2e_mix = torch.zeros_like(dev_mix)
-    h2d_bytes = torch.tensor([2 * (in_hi - in_lo) * 4], dtype=torch.float64, device=dev)
-    d2h_bytes = torch.tensor([host_out.numel() * 4], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(h2d_bytes)
-        dist.all_reduce(d2h_bytes)
-
-    host_in = host_mix[..., in_lo:in_hi].contiguous().pin_memory()   # this rank's input, resident in pinned memory
+    # End-to-end step = the public call a user makes, on HOST buffers: apply_model uploads the (pinned) mix, separates,
+    # and hands back the stems in pinned host memory (each rank the samples it produced; over all ranks the reads
+    # cover the result exactly once).  The copies are inside apply_model, hence inside the timed region.
+    last = {}
 
     def step_e2e():
-        for c in range(2):                       # row-wise: contiguous pinned <-> contiguous device runs, plain async copies
-            e2e_mix[0, c, in_lo:in_hi].copy_(host_in[0, c], non_blocking=True)
-        out = D.apply_model(model, e2e_mix, device=dev, **kw)
-        for s_ in range(4):
-            for c in range(2):
-                host_out[0, s_, c].copy_(out[0, s_, c, out_lo:out_hi], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(host_out[0, 0, 0, 0])
+        out = D.apply_model(model, host_mix, device=dev, **kw)
+        a, b = shard.owned if shard is not None else (0, length)
+        last["own"] = (a, b)
+        return float(out[0, 0, 0, a]) if b > a else 0.0
 
     def timed(fn, steps):
         barrier()
@@ -275,19 +260,34 @@ def gpu_arm(args) -> None:
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = eng.launches
     ms = timed(step_device, args.steps)
-    launches = (eng.launches - l0) * world
+    launches = torch.tensor([float(eng.launches - l0)], device=dev)
     clocks = sampler.stop() if sampler else None
-    step_e2e()
+    for _ in range(2):
+        step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    a, b = last["own"]
+    lo_seg, hi_seg = shard.block(nseg) if shard is not None else (0, nseg)
+    in_lo, in_hi = lo_seg * STRIDE, min(length, (hi_seg - 1) * STRIDE + SEG_LEN) if hi_seg > lo_seg else lo_seg * STRIDE
+    io = torch.tensor([2.0 * (in_hi - in_lo) * 4, 8.0 * (b - a) * 4], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(io)
+        dist.all_reduce(launches)
     track_s = length / SR
     value, e2e = track_s / (ms / 1e3), track_s / (ms_e2e / 1e3)
-    strict = None
-    if strict_model is not None:
-        for _ in range(2):
-            step_strict()
-        ms_strict = timed(step_strict, args.steps)
-        strict = {"mode": STRICT_MODE, "value": track_s / (ms_strict / 1e3), "unit": UNIT, "ms_per_step": ms_strict,
-                  "tolerance": "per-stem rel-L2 <= 1e-4"}
+
+    # weak-scaling companion (N > 1): 64 segments PER GPU, device-resident, same call
+    weak = None
+    if world > 1 and not args.no_weak:
+        wlen = SEGMENTS * world * STRIDE
+        wmix = synth_track(wlen).to(dev)
+
+        def step_weak():
+            return D.apply_model(model, wmix, device=dev, **kw)
+        step_weak()
+        ms_w = timed(step_weak, max(1, args.steps // 2))
+        weak = {"value": (wlen / SR) / (ms_w / 1e3), "unit": UNIT, "ms_per_step": ms_w, "segments_per_gpu": SEGMENTS,
+                "scaling": "weak"}
+        del wmix
 
     # per-kernel device time + algorithmic work of ONE more step, with events around every launch
     prof = perf.profile_step(eng, step_device)
@@ -297,18 +297,24 @@ def gpu_arm(args) -> None:
         return
     peaks = measured_peaks()
     top = prof["dominant"]
-    tensor_peak = peaks["bf16_tflops"] / 2.0            # TF32 = 1/2 of the measured bf16 GEMM rate
+    # tensor-pipe peak the dominant kernel's MMAs run against: kind::f16 (bf16) for the bf16-operand modes, half of it
+    # for kind::tf32.  `achieved` counts ALGORITHMIC flops (2*M*N*K); the split-operand modes issue three MMAs per product.
+    b16 = args.mode in ("strict", "bf16")
+    tensor_peak = peaks["bf16_tflops"] if b16 else peaks["bf16_tflops"] / 2.0
+    passes = 3 if args.mode in ("strict", "tf32x3") else 1
     if top["bound"] == "tensor":
         achieved, peak, unit = top["tflops"], tensor_peak, "TFLOP/s"
     else:
         achieved, peak, unit = top["gbs"], peaks["hbm_gbs"], "GB/s"
-    ncu = ncu_traffic(top["name"]) if args.mode == "tf32" else None
+    ncu = ncu_traffic(top["name"], args.mode)
     if ncu:   # the ncu pass ran 16-segment forwards; activations (all but the L2-resident weights) scale with the batch
         ncu["captured_at_batch"] = 16
-        ncu["bytes_per_launch"] *= args.batch / 16
+        ncu["bytes_per_launch"] *= min(args.batch, nseg // world) / 16
     roofline = {"kernel": top["name"], "bound": top["bound"], "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak, "traffic": ncu["bytes_per_launch"] if ncu else None,
                 "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "ncu": ncu,
+                "mma_passes_per_product": passes,
+                "tensor_pipe_frac_incl_passes": (passes * achieved / peak) if top["bound"] == "tensor" else None,
                 "algorithmic_bytes_per_launch": top.get("bytes_per_launch"), "peak_source": peaks["source"],
                 "share_of_step": top["share"], "launches_per_step": top["count"],
                 "avg_launch_ms": top["ms"] / max(top["count"], 1),
@@ -316,32 +322,32 @@ def gpu_arm(args) -> None:
     cpu_baseline, parity = None, None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        times, kind, (cpu_mix, cpu_out) = cpu_apply_seconds(10 * SR, 3, threads, want_output=True)
-        sec = sorted(times[1:])[len(times[1:]) // 2]
-        # the CPU run doubles as the checker: same weights, same clip, through the same public call
-        parity = {"against": kind, "clip": "10 s (2 segments), shifts=0, overlap=0.25", "per_stem_rel_l2_max": {},
-                  "tolerance": {"tf32": 1e-2, STRICT_MODE: 1e-4, "fp32": 1e-4}}
-        for name, mdl in ((args.mode, model), (STRICT_MODE, strict_model)):
-            if mdl is None:
-                continue
-            got = D.apply_model(mdl, cpu_mix.to(dev), shifts=0, split=True, overlap=0.25, device=dev).cpu()
-            err = max(float((got[0, s] - cpu_out[0, s]).norm() / cpu_out[0, s].norm()) for s in range(got.shape[1]))
-            parity["per_stem_rel_l2_max"][name] = err
-        cpu_baseline = {"value": 10.0 / sec, "unit": UNIT, "cores": threads, "kind": kind,
-                        "sample": "median of 2 x apply_model on a 10 s clip (2 segments) after 1 warm-up, "
-                                  f"{threads} threads, torch {torch.__version__} CPU fp32"}
+        nsamp = CPU_SAMPLE_SEGMENTS
+        times, kind, (cpu_mix, cpu_out) = cpu_apply_seconds(nsamp * STRIDE, 2, threads, want_output=True)
+        sec = times[-1]
+        # the CPU run doubles as the checker: same weights, same samples, through the same public call
+        got = D.apply_model(model, cpu_mix, shifts=0, split=True, overlap=0.25, device=dev, batch_size=args.batch)
+        err = max(float((got[0, s] - cpu_out[0, s]).norm() / cpu_out[0, s].norm()) for s in range(got.shape[1]))
+        parity = {"against": kind, "clip": f"first {nsamp} segments of the bench track, shifts=0, overlap=0.25",
+                  "mode": args.mode, "per_stem_rel_l2_max": err, "tolerance": TOLERANCE[args.mode],
+                  "within_tolerance": (err <= TOLERANCE[args.mode]) if TOLERANCE[args.mode] else None}
+        cpu_baseline = {"value": (nsamp * STRIDE / SR) / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                        "sample": f"second of 2 x apply_model on the first {nsamp} segments ({nsamp * STRIDE / SR:.1f} s) of "
+                                  f"the bench track, {threads} threads, torch {torch.__version__} CPU fp32"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"tf32": "tf32", "tf32x3": "tf32x3 (3-pass, fp32-accurate)"}.get(args.mode, "f32"),
-            "data": "synthetic",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": DTYPE[args.mode], "data": "synthetic",
             "config": workload_config(world, args.mode, args.batch),
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes)},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "strict": strict, "parity": parity,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(io[0]),
+                    "d2h_bytes_per_step": int(io[1]),
+                    "api": "demucs_b200.apply_model(model, pinned host mix) -> pinned host stems"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "parity": parity, "weak": weak,
             "model_roofline": {"segments_per_s": nseg / (ms / 1e3),
                                "tf32_roofline_segments_per_s_per_gpu": 1e3 / 0.742,
-                               "frac": (nseg / world / (ms / 1e3)) / (1e3 / 0.742)}}
+                               "bf16_roofline_segments_per_s_per_gpu": 1e3 / 0.377,
+                               "frac_of_tf32_model_roofline": (nseg / world / (ms / 1e3)) / (1e3 / 0.742)}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -353,10 +359,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("BD_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
-    ap.add_argument("--no-strict", action="store_true", help="skip timing the error-compensated mode beside the headline")
-    ap.add_argument("--batch", type=int, default=64, help="segments per forward (64 = one forward per step and GPU; ~36 GB)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default=os.environ.get("BD_MODE", "strict"), choices=["fp32", "tf32", "tf32x3", "strict", "bf16"],
+                    help="strict (default): error-compensated tensor-core arithmetic, per-stem rel-L2 <= 1e-4; "
+                         "bf16: reduced precision, <= 1e-2")
+    ap.add_argument("--batch", type=int, default=16, help="segments per forward")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion run")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

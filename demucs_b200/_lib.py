@@ -61,8 +61,8 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_conv_gemm_arm": [C.POINTER(GemmDesc)],
     "bd_finalize_group_stats": [_P, _P, _I, _D, _P],
     "bd_dconv_tail": [_P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
-    "bd_encoder_conv0": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "bd_dconv_conv3": [_P, _P, _P, _P, _I, _P, _LL, _I, _I, _LL, _I, _I, _P],
+    "bd_encoder_conv0": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bd_dconv_conv3": [_P, _P, _P, _P, _I, _P, _LL, _I, _I, _LL, _I, _I, _I, _P],
     "bd_dconv_expand_stats": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "bd_dconv_expand_update": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _I, _P],
     "bd_gn_gelu_apply": [_P, _P, _P, _P, _LL, _I, _LL, _I, _P],
@@ -72,6 +72,7 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_attention_workspace": [_I, _I, _I, _I, _I],
     "bd_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "bd_overlap_add": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _LL, _P, _F, _I, _P],
+    "bd_gather_segments": [_P, _P, _I, _I, _LL, _LL, _LL, _I, _I, _I, _I, _I, _P],
 }
 VALUE_CALLS = {"bd_attention_workspace"}          # entry points that return a value, not a status
 EXPORTS = ["bd_last_error", "bd_version"] + list(SIGNATURES)

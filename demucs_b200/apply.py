@@ -3,12 +3,14 @@
 Same signature, result and side effects as the reference's ``apply_model``
 (apply.py:145-322) for HTDemucs models and ``BagOfModels`` of them, but organised for a GPU:
 
-* the whole track moves to the compute device once and the separated stems move back once
-  (the reference copies every padded chunk H2D and every weighted chunk D2H, apply.py:295,312);
-* the work units (bag member, shift, segment) are enumerated up front, the segments of a pass
-  are cut into one batch tensor and run through the kernel engine ``batch_size`` at a time;
-* overlap-add, centre trim, un-shift, shift averaging and bag weighting happen in ONE gather
-  kernel per pass (K8, csrc/ola.cu) instead of one read-modify-write of the track per segment;
+* the whole track moves to the compute device once (the reference copies every padded chunk H2D and every
+  weighted chunk D2H, apply.py:295,312); a host result streams back range by range on a copy stream, under the
+  separation of the later segments;
+* the segments of a pass are cut out of the track ``batch_size`` at a time by one gather kernel
+  (``bd_gather_segments``) and the engine writes its result straight into the pass's segment store;
+* overlap-add, centre trim, un-shift, shift averaging and bag weighting happen in one gather kernel per batch
+  (K8, csrc/ola.cu) over the samples that batch completed, instead of one read-modify-write of the track per
+  segment;
 * with ``torch.distributed`` initialised and ``group`` given, the segments of every pass are
   sharded across ranks (demucs_b200/distributed.py).
 
@@ -18,6 +20,7 @@ Python's global ``random`` stream is consumed exactly as the reference does -- o
 """
 from __future__ import annotations
 
+import contextlib
 import copy
 import random
 from threading import Lock
@@ -176,65 +179,133 @@ def _segment_plan(model: HTDemucs, length: int, split: bool, overlap: float,
     return valid, min(seg_len, max(length, 1)) if not split else seg_len, stride, offsets
 
 
+def owned_window(lo_seg: int, hi_seg: int, nseg: int, seg_len: int, stride: int, length: int) -> tp.Tuple[int, int]:
+    """Window samples [w0, w1) that the holder of segments [lo_seg, hi_seg) overlap-adds: everything its segments
+    touch EXCEPT the part of its first segments that the left neighbour's last segment also reaches -- that part
+    belongs to the left neighbour, who receives the heads of these segments (distributed.Shard.exchange_heads).
+    Boundaries are block edges shifted right by the overlap seg_len - stride, so the ranges of consecutive blocks tile
+    the window."""
+    if hi_seg <= lo_seg:
+        return 0, 0
+    reach = max(seg_len - stride, 0)
+    w0 = 0 if lo_seg == 0 else min(length, lo_seg * stride + reach)
+    w1 = length if hi_seg >= nseg else min(length, hi_seg * stride + reach)
+    return w0, max(w0, w1)
+
+
 def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor, row_alpha, accumulate: bool,
              split: bool, overlap: float, transition_power: float, segment, batch_size: int,
-             notify=None, progress_bar=None, shard=None) -> None:
+             notify=None, progress_bar=None, shard=None, sink=None) -> tp.Tuple[int, int, int, int, int]:
     """Separate one window of ``track`` [B, C, Ltrack] and overlap-add it into ``out`` [B*S*C, L].
 
-    ``shard`` (``distributed.Shard``) restricts this rank to a contiguous block of the segments;
-    the left neighbour's trailing segments arrive through ``shard.exchange_halo``.
+    Segments go through the engine ``batch_size`` at a time: one gather kernel cuts the batch out of the track, the
+    forward writes straight into the pass's segment store, and one overlap-add launch finishes the window samples
+    that no later segment can touch; ``sink(lo, hi)`` is told which output samples just became final.
+    ``shard`` (``distributed.Shard``) restricts this rank to a contiguous block of the segments; the heads of the
+    right neighbours' first segments arrive through ``shard.exchange_heads``.  Returns the pass geometry
+    (nseg, seg_len, stride, window length, out_shift) from which ``Shard.combine`` derives who wrote what.
     """
     eng = model.engine()
-    B, Cc, _ = track.shape
+    B, Cc, Ltrack = track.shape
     S = len(model.sources)
     rows = B * S * Cc
     valid, seg_len, stride, offsets = _segment_plan(model, ps.length, split, overlap, segment)
     nseg = len(offsets)
     weight = transition_weight(seg_len, transition_power, track.device) if split else \
         torch.ones(seg_len, device=track.device)
+    halo = -(-seg_len // stride) - 1            # later segments whose heads reach back into a block's samples
     if shard is None:
-        lo_seg, hi_seg, first = 0, nseg, 0
+        lo_seg, hi_seg = 0, nseg
     else:
         lo_seg, hi_seg = shard.block(nseg)
-        first = max(0, lo_seg - shard.halo(seg_len, stride))   # segments reaching into this rank's samples
-    n_local = hi_seg - first
+    n_halo = min(halo, nseg - hi_seg) if hi_seg > lo_seg else 0
+    n_slots = max(hi_seg - lo_seg + n_halo, 1)
     key = ("apply", rows, valid)
-    segs = eng._buf(key, "segs", max(n_local, 1) * rows * valid).view(max(n_local, 1), rows, valid)
-    parent = TensorChunk(track, ps.offset0, ps.length)
+    segs = eng._buf(key, "segs", n_slots * rows * valid).view(n_slots, rows, valid)
     if model.cfg.t_layers > 0:
         # the reference draws random.randrange(1) inside every segment forward (transformer.py:680); every
         # rank draws for ALL segments so that sharded ranks keep identical RNG streams
         for _ in range(nseg):
             random.randrange(1)
+    w0, w1 = owned_window(lo_seg, hi_seg, nseg, seg_len, stride, ps.length)
+    out_len = out.shape[-1]
+
+    def to_out(n):      # window sample -> output sample, clipped
+        return min(max(n - ps.out_shift, 0), out_len)
+
+    pending = None
+    done = w0           # window samples [w0, done) have been overlap-added
+    sent = shard is None
     for s0 in range(lo_seg, hi_seg, batch_size):
-        idx = list(range(s0, min(s0 + batch_size, hi_seg)))
-        batch = eng._buf(key, "batch", len(idx) * B * Cc * valid).view(len(idx) * B, Cc, valid)
-        batch.zero_()
-        for j, i in enumerate(idx):
-            lo, hi, left, _ = TensorChunk(parent, offsets[i], seg_len).window(valid)
-            batch[j * B:(j + 1) * B, :, left:left + hi - lo].copy_(track[..., lo:hi])
-        for i in idx:
-            if notify:
-                notify(offsets[i], "start")
-        res = eng.forward(batch)                                   # [n*B, S, C, valid]
-        # [n, B, S*C, valid] -> rows ordered (b, s, c) per segment
-        segs[s0 - first: s0 - first + len(idx)].copy_(res.view(len(idx), rows, valid))
+        s1 = min(s0 + batch_size, hi_seg)
+        n = s1 - s0
+        batch = eng._buf(key, "batch", n * B * Cc * valid).view(n * B, Cc, valid)
+        eng._k("bd_gather_segments", ptr(track), ptr(batch), B, Cc, Ltrack, ps.offset0, ps.length, s0, n, seg_len, stride,
+               valid, eng._stream(), nbytes=8.0 * n * B * Cc * valid)
         if notify:
-            for i in idx:
+            for i in range(s0, s1):
+                notify(offsets[i], "start")
+        eng.forward(batch, out=segs[s0 - lo_seg: s1 - lo_seg])       # [n*B, S, C, valid] = [n, rows, valid]
+        if notify:
+            for i in range(s0, s1):
                 notify(offsets[i], "end")
         if progress_bar is not None:
-            progress_bar.update(len(idx))
-    n_begin, n_end = 0, ps.length
-    if shard is not None:
-        shard.exchange_halo(segs, lo_seg - first, lo_seg, hi_seg, nseg, shard.halo(seg_len, stride))
-        n_begin = lo_seg * stride
-        n_end = ps.length if hi_seg >= nseg else hi_seg * stride
-        if n_local <= 0:
-            return nseg, stride, ps.length
-    eng._k("bd_overlap_add", ptr(segs), ptr(weight), ptr(out), first, n_local, nseg, rows, valid, seg_len, stride,
+            progress_bar.update(n)
+        if not sent and s1 >= min(hi_seg, lo_seg + halo):
+            # the heads of this block's first segments are ready: ship them to the left neighbours, and post the
+            # receives for the heads this block needs from the right
+            pending = shard.exchange_heads(segs, lo_seg, hi_seg, nseg, seg_len, stride, valid, ps.length)
+            sent = True
+        # samples below s1*stride are final unless this was the block's last batch (then the heads decide)
+        upto = min(w1, s1 * stride) if s1 < hi_seg else None
+        if upto is not None and upto > done:
+            _overlap_add(eng, segs, weight, out, lo_seg, s1 - lo_seg, nseg, rows, valid, seg_len, stride, ps, done, upto,
+                         row_alpha, accumulate)
+            if sink is not None:
+                sink(to_out(done), to_out(upto))
+            done = upto
+    if shard is not None and not sent:
+        pending = shard.exchange_heads(segs, lo_seg, hi_seg, nseg, seg_len, stride, valid, ps.length)
+    if pending is not None:
+        pending()                                                      # heads have landed in the halo slots
+    if w1 > done:
+        _overlap_add(eng, segs, weight, out, lo_seg, hi_seg - lo_seg + n_halo, nseg, rows, valid, seg_len, stride, ps, done,
+                     w1, row_alpha, accumulate)
+        if sink is not None:
+            sink(to_out(done), to_out(w1))
+    return nseg, seg_len, stride, ps.length, ps.out_shift
+
+
+def _overlap_add(eng, segs, weight, out, seg_first, nseg_local, nseg, rows, valid, seg_len, stride, ps, n_begin, n_end,
+                 row_alpha, accumulate) -> None:
+    eng._k("bd_overlap_add", ptr(segs), ptr(weight), ptr(out), seg_first, nseg_local, nseg, rows, valid, seg_len, stride,
            ps.length, out.shape[-1], ps.out_shift, n_begin, n_end, ptr(row_alpha), ps.alpha, int(accumulate),
-           eng._stream(), nbytes=4.0 * rows * (n_local * min(seg_len, ps.length) + (n_end - n_begin) * (2 if accumulate else 1)))
-    return nseg, stride, ps.length
+           eng._stream(), nbytes=4.0 * rows * (n_end - n_begin) * (2 + (1 if accumulate else 0)))
+
+
+class _HostSink:
+    """Streams finished output ranges to a pinned host tensor on a side stream while later segments compute."""
+
+    def __init__(self, dev_out: torch.Tensor, device: torch.device):
+        self.dev_out = dev_out
+        self.host = torch.empty(dev_out.shape, dtype=dev_out.dtype, pin_memory=True)
+        self.stream = torch.cuda.Stream(device)
+        self.device = device
+        self.bytes = 0
+
+    def __call__(self, lo: int, hi: int) -> None:
+        if hi <= lo:
+            return
+        ev = torch.cuda.current_stream(self.device).record_event()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            for r in range(self.dev_out.shape[0]):   # contiguous device run -> contiguous pinned run: plain async copies
+                self.host[r, lo:hi].copy_(self.dev_out[r, lo:hi], non_blocking=True)
+        self.bytes += self.dev_out.shape[0] * (hi - lo) * 4
+
+    def finish(self) -> torch.Tensor:
+        self.stream.synchronize()
+        return self.host
 
 
 def apply_model(model: tp.Union[BagOfModels, Model],
@@ -254,6 +325,9 @@ def apply_model(model: tp.Union[BagOfModels, Model],
     ``num_workers`` / ``pool`` are accepted for signature compatibility; on a GPU the reference
     ignores them too (apply.py:178-182).  Extra: ``batch_size`` segments per forward, ``shard``
     (``distributed.Shard``) to split every pass across ranks.
+
+    A host ``mix`` is uploaded once (asynchronously when it is pinned) and the stems come back in a pinned host
+    tensor, streamed range by range on a copy stream while later segments are still being separated.
     """
     if isinstance(mix, TensorChunk):
         mix = mix.padded(mix.length)
@@ -269,62 +343,77 @@ def apply_model(model: tp.Union[BagOfModels, Model],
     callback_arg["models"] = len(models)
     batch, channels, length = mix.shape
     S = len(models[0].sources)
-    track = mix.to(device=device, dtype=torch.float32)             # one H2D for the whole track
-    out = torch.zeros(batch * S * channels, length, device=device)
-    totals = [0.] * S
-    bar = None
-    plans: tp.Set[tp.Optional[tp.Tuple[int, int, int]]] = set()     # segment plans of the passes (None: shifted)
-    for mi, sub in enumerate(models):
-        original_device = next(iter(sub.parameters())).device
-        sub.to(device)
-        sub.eval()
+    on_cuda = device.type == "cuda"
+    guard = torch.cuda.device(device) if on_cuda else contextlib.nullcontext()
+    with guard:
+        to_host = on_cuda and mix.device.type == "cpu"
+        track = mix.to(device=device, dtype=torch.float32, non_blocking=to_host and mix.is_pinned())   # one H2D
+        n_passes = len(models) * max(shifts, 1)
+        # every pass but the first accumulates; a sharded multi-pass run also accumulates into ranges its first pass
+        # did not write (the owned ranges move with the shift), so only that case needs a zero fill
+        alloc = torch.zeros if (shard is not None and n_passes > 1) else torch.empty
+        out = alloc(batch * S * channels, length, device=device)
+        totals = [0.] * S
         if bag_weights is not None:
-            # estimates += w[m][k] * out_m[:, k]; afterwards /= totals[k]  (apply.py:219-228)
-            for k, w in enumerate(bag_weights[mi]):
-                totals[k] += w
-            ra = torch.tensor(bag_weights[mi], dtype=torch.float32).view(1, S, 1).expand(batch, S, channels)
-            row_alpha = ra.reshape(-1).contiguous().to(device)
-        else:
-            row_alpha = None
-        passes: tp.List[_Pass] = []
-        src = track
-        if shifts:
-            max_shift = int(0.5 * sub.samplerate)
-            src = tensor_chunk(track).padded(length + 2 * max_shift)
-        for si in range(max(shifts, 1)):
-            if shifts:
-                offset = random.randint(0, max_shift)
-                ps = _Pass(mi, si, offset, length + max_shift - offset, max_shift - offset, 1.0 / shifts)
+            for w_m in bag_weights:
+                for k, w in enumerate(w_m):
+                    totals[k] += w
+        bar = None
+        sink = _HostSink(out, device) if (to_host and n_passes == 1) else None
+        written: tp.List[tp.Tuple[int, int]] = []
+        n_done = 0
+        for mi, sub in enumerate(models):
+            original_device = next(iter(sub.parameters())).device
+            sub.to(device)
+            sub.eval()
+            if bag_weights is not None:
+                # estimates += w[m][k] * out_m[:, k]; afterwards /= totals[k]  (apply.py:219-228), folded into the
+                # per-row factor of the overlap-add
+                ra = torch.tensor([w / t for w, t in zip(bag_weights[mi], totals)], dtype=torch.float32)
+                row_alpha = ra.view(1, S, 1).expand(batch, S, channels).reshape(-1).contiguous().to(device)
             else:
-                ps = _Pass(mi, 0, 0, length, 0, 1.0)
-            passes.append(ps)
+                row_alpha = None
+            src = track
+            if shifts:
+                max_shift = int(0.5 * sub.samplerate)
+                src = tensor_chunk(track).padded(length + 2 * max_shift)
+            for si in range(max(shifts, 1)):
+                if shifts:
+                    # drawn where the reference draws it (apply.py:245), between the segment forwards of consecutive
+                    # shifts (which consume the stream too); sharded ranks must cut the same windows: rank 0's draw wins
+                    offset = random.randint(0, max_shift)
+                    if shard is not None:
+                        offset = shard.agree([offset])[0]
+                    ps = _Pass(mi, si, offset, length + max_shift - offset, max_shift - offset, 1.0 / shifts)
+                else:
+                    ps = _Pass(mi, 0, 0, length, 0, 1.0)
 
-            def notify(seg_offset, state, ps=ps):
-                if callback is not None:
-                    with lock:
-                        callback(_replace_dict(callback_arg, ("model_idx_in_bag", ps.model_idx),
-                                               ("shift_idx", ps.shift_idx), ("segment_offset", seg_offset),
-                                               ("state", state)))
+                def notify(seg_offset, state, ps=ps):
+                    if callback is not None:
+                        with lock:
+                            callback(_replace_dict(callback_arg, ("model_idx_in_bag", ps.model_idx),
+                                                   ("shift_idx", ps.shift_idx), ("segment_offset", seg_offset),
+                                                   ("state", state)))
 
-            if progress and split and bar is None:
-                import tqdm
-                seg_s = float(sub.segment if segment is None else segment)
-                scale = float(format((1 - overlap) * seg_s, ".2f"))
-                bar = tqdm.tqdm(unit_scale=scale, ncols=120, unit='seconds')
-            plan = run_pass(sub, src, ps, out, row_alpha, accumulate=(mi > 0 or si > 0 or shard is not None),
-                     split=split, overlap=overlap,
-                     transition_power=transition_power, segment=segment, batch_size=batch_size,
-                     notify=notify if callback is not None else None, progress_bar=bar, shard=shard)
-            plans.add(plan if not shifts else None)
-        sub.to(original_device)
-    if bar is not None:
-        bar.close()
-    if shard is not None:
-        # ranks hold disjoint sample ranges of every pass: one all-gather when all passes share one unshifted
-        # segment plan, else an all-reduce of the zero-padded pieces
-        only = next(iter(plans)) if len(plans) == 1 else None
-        shard.combine(out, only)
-    out = out.view(batch, S, channels, length)
-    if bag_weights is not None:
-        out /= torch.tensor(totals, dtype=torch.float32, device=device).view(1, S, 1, 1)
-    return out.to(mix.device)                                      # one D2H for all stems
+                if progress and split and bar is None:
+                    import tqdm
+                    seg_s = float(sub.segment if segment is None else segment)
+                    scale = float(format((1 - overlap) * seg_s, ".2f"))
+                    bar = tqdm.tqdm(unit_scale=scale, ncols=120, unit='seconds')
+                written.append(run_pass(sub, src, ps, out, row_alpha, accumulate=n_done > 0, split=split, overlap=overlap,
+                                        transition_power=transition_power, segment=segment, batch_size=batch_size,
+                                        notify=notify if callback is not None else None, progress_bar=bar, shard=shard,
+                                        sink=sink))
+                n_done += 1
+            sub.to(original_device)
+        if bar is not None:
+            bar.close()
+        own = (0, length)
+        if shard is not None:
+            own = shard.combine(out, written)          # slivers to their owners, then gather as the shard is set up
+        if not to_host:
+            return out.view(batch, S, channels, length).to(mix.device)
+        if sink is None:
+            sink = _HostSink(out, device)
+            sink(*own)
+        return sink.finish().view(batch, S, channels, length)

@@ -470,11 +470,23 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// Error-compensated form ("3xTF32", the strict modes): x = hi + lo with hi = rn_tf32(x) and lo = x - hi (exact in fp32;
+// the tensor core reads its top 10 mantissa bits), product = lo*hi + hi*lo + hi*hi, small terms first.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32x3_16x8x8(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                                  uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32_16x8x8(c, al, bh0, bh1);
+  mma_tf32_16x8x8(c, ah, bl0, bl1);
+  mma_tf32_16x8x8(c, ah, bh0, bh1);
+}
 
 // CTA = 8 warps that share one block of 96 interleaved columns (48 channels) of the expansion: its weights sit in
 // shared memory as tf32 [96][8*KS + 4] (the pitch makes the B-fragment loads conflict-free), every warp walks
 // 32-row tiles.  KS = k-steps of 8: hid 6 -> 1, 12 -> 2, 24 -> 4, 48 -> 7 (row `hid` carries the bias).
-template <int HID>
+template <int HID, bool X3>
 __global__ void __launch_bounds__(256) dconv_update_mma_kernel(
     const float* __restrict__ h, int ldh, const float* __restrict__ mr1, const float* __restrict__ g1,
     const float* __restrict__ be1, const float* __restrict__ w2t /*[hid][2C]*/, const float* __restrict__ b2,
@@ -487,15 +499,20 @@ __global__ void __launch_bounds__(256) dconv_update_mma_kernel(
   const int N = 2 * C;
   const int n_lo = blockIdx.y * NB, c_lo = blockIdx.y * CB;
   extern __shared__ __align__(16) float sm[];
-  uint32_t* sW = reinterpret_cast<uint32_t*>(sm);  // [NB][KP] tf32
-  float* sG = sm + NB * KP;                        // [NB]
+  uint32_t* sW = reinterpret_cast<uint32_t*>(sm);  // [NB][KP] tf32 (X3: then the lo parts, [NB][KP])
+  uint32_t* sWl = sW + NB * KP;
+  float* sG = sm + (X3 ? 2 : 1) * NB * KP;         // [NB]
   float* sBe = sG + NB;                            // [NB]
   float* sS = sBe + NB;                            // [CB]
   float* sT = sS + CB + (threadIdx.x >> 5) * (32 * LDT);   // [32 rows][LDT] per warp
   for (int i = threadIdx.x; i < NB * 8 * KS; i += 256) {
     const int n = i / (8 * KS), k = i - n * (8 * KS);
     const float w = k < HID ? __ldg(w2t + (size_t)k * N + n_lo + n) : (k == HID ? __ldg(b2 + n_lo + n) : 0.f);
-    sW[n * KP + k] = to_tf32(w);
+    if (X3) {
+      split_tf32(w, sW[n * KP + k], sWl[n * KP + k]);
+    } else {
+      sW[n * KP + k] = to_tf32(w);
+    }
   }
   for (int i = threadIdx.x; i < NB; i += 256) {
     sG[i] = __ldg(g2 + n_lo + i);
@@ -516,7 +533,7 @@ __global__ void __launch_bounds__(256) dconv_update_mma_kernel(
   for (long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
     const long long m0 = tile * 32;
     // this thread's 4 rows: gid, gid + 8 (fragment 0), gid + 16, gid + 24 (fragment 1)
-    uint32_t ah[2][KS][4];
+    uint32_t ah[2][KS][4], al[X3 ? 2 : 1][X3 ? KS : 1][4];
     float m2[4], r2[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -534,7 +551,11 @@ __global__ void __launch_bounds__(256) dconv_update_mma_kernel(
         const int k = 8 * (j >> 1) + tig + 4 * (j & 1);
         float v = k == HID ? 1.f : 0.f;
         if (k < HID) v = bd_gelu(fmaf((__ldg(hr + k) - mean1) * rstd1, ga[j], bea[j]));
-        ah[f][j >> 1][2 * (j & 1) + hi8] = to_tf32(v);
+        if (X3) {
+          split_tf32(v, ah[f][j >> 1][2 * (j & 1) + hi8], al[X3 ? f : 0][X3 ? (j >> 1) : 0][2 * (j & 1) + hi8]);
+        } else {
+          ah[f][j >> 1][2 * (j & 1) + hi8] = to_tf32(v);
+        }
       }
     }
 #pragma unroll
@@ -547,8 +568,14 @@ __global__ void __launch_bounds__(256) dconv_update_mma_kernel(
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint32_t b0 = sW[(8 * nt + gid) * KP + 8 * ks + tig], b1 = sW[(8 * nt + gid) * KP + 8 * ks + tig + 4];
-        mma_tf32_16x8x8(c[0], ah[0][ks], b0, b1);
-        mma_tf32_16x8x8(c[1], ah[1][ks], b0, b1);
+        if (X3) {
+          const uint32_t l0 = sWl[(8 * nt + gid) * KP + 8 * ks + tig], l1 = sWl[(8 * nt + gid) * KP + 8 * ks + tig + 4];
+          mma_tf32x3_16x8x8(c[0], ah[0][ks], al[0][X3 ? ks : 0], b0, b1, l0, l1);
+          mma_tf32x3_16x8x8(c[1], ah[1][ks], al[X3 ? 1 : 0][X3 ? ks : 0], b0, b1, l0, l1);
+        } else {
+          mma_tf32_16x8x8(c[0], ah[0][ks], b0, b1);
+          mma_tf32_16x8x8(c[1], ah[1][ks], b0, b1);
+        }
       }
 #pragma unroll
       for (int f = 0; f < 2; ++f) {
@@ -587,7 +614,7 @@ __global__ void __launch_bounds__(256) dconv_update_mma_kernel(
   }
 }
 
-template <int HID>
+template <int HID, bool X3>
 int launch_update_mma(const float* h, int ldh, const float* mr1, const float* g1, const float* be1, const float* w2t,
                       const float* b2, const float* mr2, const float* g2, const float* be2, const float* scale, float* x,
                       long long M, int C, long long rpi, int spi, cudaStream_t st) {
@@ -596,13 +623,13 @@ int launch_update_mma(const float* h, int ldh, const float* mr1, const float* g1
   long long gx = ((M + 31) / 32 + 7) / 8;
   const long long cap = (148LL * 4 + nblk - 1) / nblk;          // ~4 CTAs per SM over all column blocks
   if (gx > cap) gx = cap;
-  const int smem = (96 * KP + 2 * 96 + 48 + 8 * 32 * 52) * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(dconv_update_mma_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = ((X3 ? 2 : 1) * 96 * KP + 2 * 96 + 48 + 8 * 32 * 52) * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(dconv_update_mma_kernel<HID, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     bd_set_error("bd_dconv_expand_update: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return BD_ERR_CUDA;
   }
-  dconv_update_mma_kernel<HID><<<dim3((unsigned)gx, nblk), 256, smem, st>>>(h, ldh, mr1, g1, be1, w2t, b2, mr2, g2, be2,
+  dconv_update_mma_kernel<HID, X3><<<dim3((unsigned)gx, nblk), 256, smem, st>>>(h, ldh, mr1, g1, be1, w2t, b2, mr2, g2, be2,
                                                                            scale, x, M, C, rpi, spi);
   return bd_check_launch("dconv_update_mma_kernel");
 }
@@ -614,22 +641,29 @@ int launch_update_mma(const float* h, int ldh, const float* mr1, const float* g1
 // (N >= 16, its epilogue, a 16-wide padded h) costs more than the contraction.  Here the weights live in B
 // fragments, a warp takes 32 rows, every lane reads float4 runs of the input row (the K index is permuted so that
 // a lane's four fragment elements of two k-steps are one contiguous float4) and h is stored 8 floats wide.
-template <int C>
-__global__ void __launch_bounds__(256, 2) dconv_conv3_mma_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+template <int C, bool X3>
+__global__ void __launch_bounds__(256, X3 ? 1 : 2) dconv_conv3_mma_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                               const float* __restrict__ b1, float* __restrict__ h,
                                                               double* __restrict__ sums, long long M, long long rpi,
                                                               int spi, int dil) {
   constexpr int HID = 6, KSC = C / 8, NP = C / 16;            // k-steps / float4 pairs per tap
   const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   // B fragment of k-step (tap, 2p + s): b0 <- channel 16p + 4tig + 2s, b1 <- channel 16p + 4tig + 2s + 1; column gid
-  uint32_t bf[3 * KSC][2];
+  uint32_t bf[3 * KSC][2], bl[X3 ? 3 * KSC : 1][2];
 #pragma unroll
   for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
     for (int ks = 0; ks < KSC; ++ks) {
       const int ch = 16 * (ks >> 1) + 4 * tig + 2 * (ks & 1);
-      bf[tap * KSC + ks][0] = gid < HID ? to_tf32(__ldg(w1 + (size_t)gid * 3 * C + tap * C + ch)) : 0u;
-      bf[tap * KSC + ks][1] = gid < HID ? to_tf32(__ldg(w1 + (size_t)gid * 3 * C + tap * C + ch + 1)) : 0u;
+      const float w0 = gid < HID ? __ldg(w1 + (size_t)gid * 3 * C + tap * C + ch) : 0.f;
+      const float w1v = gid < HID ? __ldg(w1 + (size_t)gid * 3 * C + tap * C + ch + 1) : 0.f;
+      if (X3) {
+        split_tf32(w0, bf[tap * KSC + ks][0], bl[X3 ? tap * KSC + ks : 0][0]);
+        split_tf32(w1v, bf[tap * KSC + ks][1], bl[X3 ? tap * KSC + ks : 0][1]);
+      } else {
+        bf[tap * KSC + ks][0] = to_tf32(w0);
+        bf[tap * KSC + ks][1] = to_tf32(w1v);
+      }
     }
   const float bz0 = 2 * tig < HID ? __ldg(b1 + 2 * tig) : 0.f, bz1 = 2 * tig + 1 < HID ? __ldg(b1 + 2 * tig + 1) : 0.f;
   const long long T = rpi / spi;
@@ -664,12 +698,26 @@ __global__ void __launch_bounds__(256, 2) dconv_conv3_mma_kernel(const float* __
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
           // rows 2f (gid + 16f) and 2f+1 (gid + 8 + 16f); a0/a1: k = tig of the two rows, a2/a3: k = tig + 4
+          if (X3) {
+            const float fe[4] = {v[2 * f][p].x, v[2 * f + 1][p].x, v[2 * f][p].y, v[2 * f + 1][p].y};
+            const float fo[4] = {v[2 * f][p].z, v[2 * f + 1][p].z, v[2 * f][p].w, v[2 * f + 1][p].w};
+            uint32_t eh[4], el[4], oh[4], ol[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              split_tf32(fe[e], eh[e], el[e]);
+              split_tf32(fo[e], oh[e], ol[e]);
+            }
+            const int k0 = tap * KSC + 2 * p, kl0 = X3 ? k0 : 0, kl1 = X3 ? k0 + 1 : 0;
+            mma_tf32x3_16x8x8(c[f], eh, el, bf[k0][0], bf[k0][1], bl[kl0][0], bl[kl0][1]);
+            mma_tf32x3_16x8x8(c[f], oh, ol, bf[k0 + 1][0], bf[k0 + 1][1], bl[kl1][0], bl[kl1][1]);
+          } else {
           const uint32_t a_even[4] = {to_tf32(v[2 * f][p].x), to_tf32(v[2 * f + 1][p].x), to_tf32(v[2 * f][p].y),
                                       to_tf32(v[2 * f + 1][p].y)};
           const uint32_t a_odd[4] = {to_tf32(v[2 * f][p].z), to_tf32(v[2 * f + 1][p].z), to_tf32(v[2 * f][p].w),
                                      to_tf32(v[2 * f + 1][p].w)};
           mma_tf32_16x8x8(c[f], a_even, bf[tap * KSC + 2 * p][0], bf[tap * KSC + 2 * p][1]);
           mma_tf32_16x8x8(c[f], a_odd, bf[tap * KSC + 2 * p + 1][0], bf[tap * KSC + 2 * p + 1][1]);
+          }
         }
       }
     }
@@ -725,8 +773,8 @@ __global__ void __launch_bounds__(256, 2) dconv_conv3_mma_kernel(const float* __
 //        floats starting at position 4*i0 - 2; K index permuted so that a lane reads float4 = one position.
 //   CM = true  (time branch):      x [B, 2, Jin] channel-major (the raw mix), k-step = channel, k = tap.
 // Positions outside [0, Jin) read as zero AFTER the normalisation (zero padding of the normalised tensor).
-template <int CIN, bool CM>
-__global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __restrict__ x, const float* __restrict__ norm,
+template <int CIN, bool CM, bool X3>
+__global__ void __launch_bounds__(256, X3 ? 1 : 2) conv_first_mma_kernel(const float* __restrict__ x, const float* __restrict__ norm,
                                                                 int norm_stride, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* __restrict__ out,
                                                                 long long M, int I1, int Io, int Jin) {
@@ -735,7 +783,7 @@ __global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __r
   // logical k of fragment element (ks, tig, half) -> (tap, channel)
   //   CM:  ks = channel, tap = tig + 4*half
   //   !CM: pair p = ks>>1, position-in-window = 4p + tig (one float4 = 4 channels), channel = 2*(ks&1) + half
-  uint32_t bf[KS][NT][2];
+  uint32_t bf[KS][NT][2], bl[X3 ? KS : 1][NT][2];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -744,7 +792,9 @@ __global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __r
       for (int half = 0; half < 2; ++half) {
         const int tap = CM ? tig + 4 * half : 4 * (ks >> 1) + tig;
         const int ch = CM ? ks : 2 * (ks & 1) + half;
-        bf[ks][nt][half] = to_tf32(__ldg(w + (size_t)(8 * nt + gid) * K + tap * CIN + ch));
+        const float wv = __ldg(w + (size_t)(8 * nt + gid) * K + tap * CIN + ch);
+        if (X3) split_tf32(wv, bf[ks][nt][half], bl[X3 ? ks : 0][nt][half]);
+        else bf[ks][nt][half] = to_tf32(wv);
       }
   float bz[NT][2];
 #pragma unroll
@@ -757,7 +807,11 @@ __global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __r
   const long long wstride = (long long)gridDim.x * 8;
   for (long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
     const long long m0 = tile * 32;
-    uint32_t a[2][KS][4];
+    uint32_t a[2][KS][4], al[X3 ? 2 : 1][X3 ? KS : 1][4];
+    auto put = [&](int f, int ks, int e, float v) {
+      if (X3) split_tf32(v, a[f][ks][e], al[X3 ? f : 0][X3 ? ks : 0][e]);
+      else a[f][ks][e] = to_tf32(v);
+    };
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const long long m = m0 + gid + 8 * q;
@@ -775,7 +829,7 @@ __global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __r
           for (int half = 0; half < 2; ++half) {
             const int pos = 4 * i0 - 2 + tig + 4 * half;
             const float v = (pos >= 0 && pos < Jin) ? (__ldg(src + (size_t)ks * Jin + pos) - mean) * rstd : 0.f;
-            a[f][ks][2 * half + hi8] = to_tf32(v);
+            put(f, ks, 2 * half + hi8, v);
           }
       } else {
         const float* src = x + (((size_t)b * I1 + i1) * Jin) * CIN;
@@ -787,10 +841,10 @@ __global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __r
             v = __ldg(reinterpret_cast<const float4*>(src + (size_t)pos * CIN));
             v = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
           }
-          a[f][2 * p][hi8] = to_tf32(v.x);          // ks = 2p:   channels 0 (half 0), 1 (half 1)
-          a[f][2 * p][2 + hi8] = to_tf32(v.y);
-          a[f][2 * p + 1][hi8] = to_tf32(v.z);      // ks = 2p+1: channels 2, 3
-          a[f][2 * p + 1][2 + hi8] = to_tf32(v.w);
+          put(f, 2 * p, hi8, v.x);                  // ks = 2p:   channels 0 (half 0), 1 (half 1)
+          put(f, 2 * p, 2 + hi8, v.y);
+          put(f, 2 * p + 1, hi8, v.z);              // ks = 2p+1: channels 2, 3
+          put(f, 2 * p + 1, 2 + hi8, v.w);
         }
       }
     }
@@ -800,7 +854,13 @@ __global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __r
       for (int f = 0; f < 2; ++f) {
         float c[4] = {bz[nt][0], bz[nt][1], bz[nt][0], bz[nt][1]};
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) mma_tf32_16x8x8(c, a[f][ks], bf[ks][nt][0], bf[ks][nt][1]);
+        for (int ks = 0; ks < KS; ++ks) {
+          if (X3)
+            mma_tf32x3_16x8x8(c, a[f][ks], al[X3 ? f : 0][X3 ? ks : 0], bf[ks][nt][0], bf[ks][nt][1], bl[X3 ? ks : 0][nt][0],
+                              bl[X3 ? ks : 0][nt][1]);
+          else
+            mma_tf32_16x8x8(c, a[f][ks], bf[ks][nt][0], bf[ks][nt][1]);
+        }
 #pragma unroll
         for (int hi8 = 0; hi8 < 2; ++hi8) {
           const long long m = m0 + gid + 8 * (2 * f + hi8);
@@ -818,7 +878,7 @@ __global__ void __launch_bounds__(256, 2) conv_first_mma_kernel(const float* __r
 extern "C" {
 
 int bd_encoder_conv0(const float* x, int channel_major, const float* norm, int norm_stride, const float* w, const float* bias,
-                     float* out, int B, int I1, int Io, int Jin, int cin, int cout, void* stream) {
+                     float* out, int B, int I1, int Io, int Jin, int cin, int cout, int math, void* stream) {
   BD_REQUIRE(cout == 48 && ((channel_major && cin == 2 && I1 == 1) || (!channel_major && cin == 4)),
              "bd_encoder_conv0: only the htdemucs first layers are built (cin=%d cout=%d channel_major=%d)", cin, cout, channel_major);
   BD_REQUIRE(B > 0 && I1 > 0 && Io > 0 && Jin > 0 && 4 * (Io - 1) - 2 < Jin, "bd_encoder_conv0: bad sizes");
@@ -826,23 +886,32 @@ int bd_encoder_conv0(const float* x, int channel_major, const float* norm, int n
   const long long M = (long long)B * I1 * Io;
   long long grid = ((M + 31) / 32 + 7) / 8;
   if (grid > 148LL * 2 * 4) grid = 148LL * 2 * 4;
-  if (channel_major)
-    conv_first_mma_kernel<2, true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
-  else
-    conv_first_mma_kernel<4, false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
+  const bool x3 = math == BD_MATH_TF32X3 || math == BD_MATH_BF16X3;
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (channel_major) {
+    if (x3) conv_first_mma_kernel<2, true, true><<<(unsigned)grid, 256, 0, st>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
+    else conv_first_mma_kernel<2, true, false><<<(unsigned)grid, 256, 0, st>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
+  } else {
+    if (x3) conv_first_mma_kernel<4, false, true><<<(unsigned)grid, 256, 0, st>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
+    else conv_first_mma_kernel<4, false, false><<<(unsigned)grid, 256, 0, st>>>(x, norm, norm_stride, w, bias, out, M, I1, Io, Jin);
+  }
   return bd_check_launch("conv_first_mma_kernel");
 }
 
 int bd_dconv_conv3(const float* x, const float* w1, const float* b1, float* h, int ldh, double* sums1, long long M, int C,
-                   int hid, long long rows_per_item, int slabs_per_item, int dilation, void* stream) {
+                   int hid, long long rows_per_item, int slabs_per_item, int dilation, int math, void* stream) {
   BD_REQUIRE(hid == 6 && C == 48 && ldh == 8, "bd_dconv_conv3: only hid 6 / C 48 / ldh 8 is built (hid=%d C=%d ldh=%d)", hid, C, ldh);
   BD_REQUIRE(M > 0 && rows_per_item > 0 && slabs_per_item > 0 && rows_per_item % slabs_per_item == 0 && dilation > 0,
              "bd_dconv_conv3: bad sizes");
   BD_REQUIRE((((uintptr_t)x | (uintptr_t)h) & 15) == 0, "bd_dconv_conv3: unaligned tensor");
   long long grid = ((M + 31) / 32 + 7) / 8;
   if (grid > 148LL * 2 * 4) grid = 148LL * 2 * 4;     // 2 resident CTAs per SM, 4 rounds
-  dconv_conv3_mma_kernel<48><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, w1, b1, h, sums1, M, rows_per_item,
-                                                                                slabs_per_item, dilation);
+  if (math == BD_MATH_TF32X3 || math == BD_MATH_BF16X3)
+    dconv_conv3_mma_kernel<48, true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, w1, b1, h, sums1, M, rows_per_item,
+                                                                                       slabs_per_item, dilation);
+  else
+    dconv_conv3_mma_kernel<48, false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, w1, b1, h, sums1, M, rows_per_item,
+                                                                                        slabs_per_item, dilation);
   return bd_check_launch("dconv_conv3_mma_kernel");
 }
 
@@ -863,14 +932,18 @@ int bd_dconv_expand_update(const float* h, int ldh, int hid, const float* mean_r
                            const float* gamma2, const float* beta2, const float* scale, float* x, long long M, int C,
                            long long rows_per_item, int slabs_per_item, int math, void* stream) {
   BD_REQUIRE(hid > 0 && hid <= MAX_HID && C % 2 == 0 && ldh >= hid && M > 0, "bd_dconv_expand_update: bad sizes (hid=%d C=%d)", hid, C);
-  if (math == BD_MATH_TF32 && C % 48 == 0 && (hid == 6 || hid == 12 || hid == 24 || hid == 48)) {
 #define BD_MMA_ARGS h, ldh, mean_rstd1, gamma1, beta1, w2t, b2, mean_rstd2, gamma2, beta2, scale, x, M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream
-    if (hid == 6) return launch_update_mma<6>(BD_MMA_ARGS);
-    if (hid == 12) return launch_update_mma<12>(BD_MMA_ARGS);
-    if (hid == 24) return launch_update_mma<24>(BD_MMA_ARGS);
-    return launch_update_mma<48>(BD_MMA_ARGS);
-#undef BD_MMA_ARGS
+  if ((math == BD_MATH_TF32 || math == BD_MATH_BF16) && C % 48 == 0 && (hid == 6 || hid == 12 || hid == 24 || hid == 48)) {
+    if (hid == 6) return launch_update_mma<6, false>(BD_MMA_ARGS);
+    if (hid == 12) return launch_update_mma<12, false>(BD_MMA_ARGS);
+    if (hid == 24) return launch_update_mma<24, false>(BD_MMA_ARGS);
+    return launch_update_mma<48, false>(BD_MMA_ARGS);
   }
+  // strict modes: the same kernel with hi/lo operand splits in registers (three mma.sync per product) where it beats
+  // the exact FFMA kernel below (measured: hid 6 1.31 vs 1.74 ms; hid 12 1.30 vs 1.08 ms per 4 launches at 16 segments)
+  if ((math == BD_MATH_TF32X3 || math == BD_MATH_BF16X3) && C % 48 == 0 && hid == 6)
+    return launch_update_mma<6, true>(BD_MMA_ARGS);
+#undef BD_MMA_ARGS
   return launch_expand<true>(h, ldh, hid, mean_rstd1, gamma1, beta1, w2t, b2, nullptr, mean_rstd2, gamma2, beta2, scale, x,
                              M, C, rows_per_item, slabs_per_item, (cudaStream_t)stream);
 }

@@ -80,3 +80,42 @@ extern "C" int bd_overlap_add(const float* segs, const float* weight, float* out
       n_end, row_alpha, alpha, accumulate);
   return bd_check_launch("overlap_add_kernel");
 }
+
+// ---- segment gather: the input side of the batcher ------------------------------------------------------------
+// batch[(j*B + b), c, t] = track[b, c, start_j + t] (zero outside [0, track_len)), j < nseg_batch, for the segments
+// i = seg_first + j of a pass whose window starts at `offset0` in the track: segment i covers window samples
+// [i*stride, i*stride + n_i), n_i = min(length - i*stride, seg_len), and is centred in `valid` samples --
+// start_j = offset0 + i*stride - (valid - n_i)/2 -- exactly TensorChunk.padded (reference apply.py:108-124): the
+// padding is real signal where the track has it, zeros beyond its ends.  One launch per forward batch instead of one
+// copy per segment.
+namespace {
+__global__ void gather_segments_kernel(const float* __restrict__ track, float* __restrict__ batch, int B, int C,
+                                       long long track_len, long long offset0, long long length, int seg_first,
+                                       int seg_len, int stride, int valid) {
+  const int j = blockIdx.z, bc = blockIdx.y;                 // bc = b*C + c
+  const long long i = seg_first + j;
+  const long long rem = length - i * stride;
+  const int n_i = rem < seg_len ? (int)rem : seg_len;
+  const long long start = offset0 + i * stride - (valid - n_i) / 2;
+  const float* src = track + (size_t)bc * track_len;
+  float* dst = batch + ((size_t)j * B * C + bc) * valid;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < valid; t += gridDim.x * blockDim.x) {
+    const long long s = start + t;
+    dst[t] = (s >= 0 && s < track_len) ? __ldg(src + s) : 0.f;
+  }
+}
+}  // namespace
+
+extern "C" int bd_gather_segments(const float* track, float* batch, int B, int C, long long track_len, long long offset0,
+                                  long long length, int seg_first, int nseg_batch, int seg_len, int stride, int valid,
+                                  void* stream) {
+  BD_REQUIRE(B > 0 && C > 0 && B * C <= 65535 && nseg_batch > 0 && nseg_batch <= 65535 && valid > 0 && seg_len > 0 &&
+                 seg_len <= valid && stride > 0 && track_len > 0 && length > 0,
+             "bd_gather_segments: bad sizes");
+  BD_REQUIRE((long long)(seg_first + nseg_batch - 1) * stride < length, "bd_gather_segments: segment beyond the window");
+  int gx = bd_cdiv(valid, 256 * 4);
+  if (gx > 1024) gx = 1024;
+  gather_segments_kernel<<<dim3(gx, B * C, nseg_batch), 256, 0, (cudaStream_t)stream>>>(
+      track, batch, B, C, track_len, offset0, length, seg_first, seg_len, stride, valid);
+  return bd_check_launch("gather_segments_kernel");
+}

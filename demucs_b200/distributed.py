@@ -4,13 +4,20 @@ The reference has no multi-GPU inference path (its only parallelism is a CPU thr
 apply.py:178-182); SURVEY.md section 8e defines the B200-native replacement.  The unit of work
 is a segment forward; all units of a (bag member, shift) pass are independent
 (apply.py:278-284), so every pass is split into contiguous blocks of segments, one per rank,
-with the model weights replicated.  The only data-path exchange is what the overlap-add
-needs: rank r owns the output samples [lo_r*stride, hi_r*stride) and those also receive the
-tails of the ``halo`` segments just left of its block, which the left neighbour sends
-(point-to-point, ~11 MB per segment).  Afterwards every rank holds a disjoint range of the
-result; ``combine`` exchanges the pieces with one all-gather (or, when the shift trick moves the
-owned ranges from pass to pass, sums the zero-padded pieces with one all-reduce).  The overlap-add kernel is given the block's global position, so the values
-are bit-identical to a single-GPU run.
+with the model weights replicated.  The only data-path exchange is what the overlap-add needs:
+
+* a rank overlap-adds every sample its segments touch except the stretch its FIRST segment shares with the left
+  neighbour's last one; that stretch belongs to the left neighbour, who receives just the HEAD of the segment --
+  ``seg_len - stride`` samples per row (2.75 MB for htdemucs), not the segment.  Heads are the first thing a rank
+  computes and the last thing its neighbour needs, so the transfer hides under the forward passes;
+* with several passes (shift trick, bag members) the sample ranges a rank writes move from pass to pass by at
+  most the shift; ownership is fixed to the ranges of the first pass and the slivers outside it are sent to
+  their owners and added (``combine``) -- no all-reduce of zero-padded full-length tensors;
+* what happens to the finished, disjoint ranges is the caller's choice (``gather``): left in place ("none": each
+  rank hands its own range to the host, nothing crosses NVLink), collected on rank 0 ("root"), or replicated
+  on every rank ("all").
+
+The overlap-add kernel is given the block's global position, so the values are those of a single-GPU run.
 """
 from __future__ import annotations
 
@@ -21,12 +28,16 @@ import torch.distributed as dist
 
 
 class Shard:
-    def __init__(self, group=None):
+    def __init__(self, group=None, gather: str = "all"):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        if gather not in ("all", "root", "none"):
+            raise ValueError("gather must be 'all', 'root' or 'none'")
         self.group = group
+        self.gather = gather
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.owned: tp.Tuple[int, int] = (0, 0)      # output samples this rank holds after the last apply_model
 
     # ---- partitioning -----------------------------------------------------------------------
     def block_of(self, rank: int, nseg: int) -> tp.Tuple[int, int]:
@@ -41,65 +52,159 @@ class Shard:
 
     @staticmethod
     def halo(seg_len: int, stride: int) -> int:
-        """Segments to the left of a block whose windows reach into it: ceil(seg_len/stride) - 1."""
+        """Segments next to a block whose windows reach into it: ceil(seg_len/stride) - 1."""
         return -(-seg_len // stride) - 1
-
-    # ---- data-path exchange -------------------------------------------------------------------
-    def exchange_halo(self, segs: torch.Tensor, n_halo: int, lo: int, hi: int, nseg: int, halo: int) -> None:
-        """segs [n_local, rows, valid] = [halo slots | own block [lo, hi)].  Fill the ``n_halo`` halo
-        slots with the segments just left of ``lo`` (owned by lower ranks) and send this rank's
-        trailing segments to the ranks whose halo they are.  Every rank derives the same schedule."""
-        if self.world == 1:
-            return
-        blocks = [self.block_of(r, nseg) for r in range(self.world)]
-
-        def owner(g):
-            return next(q for q, (ql, qh) in enumerate(blocks) if ql <= g < qh)
-
-        ops = []
-        for r, (l, h) in enumerate(blocks):
-            if h == l:
-                continue                                # empty block: owns no samples, needs no halo
-            for g in range(max(0, l - halo), l):        # segment g is part of rank r's halo
-                o = owner(g)
-                if o == self.rank and r != self.rank:
-                    ops.append(dist.P2POp(dist.isend, segs[n_halo + (g - lo)], self._peer(r), self.group))
-                elif r == self.rank and o != self.rank:
-                    ops.append(dist.P2POp(dist.irecv, segs[g - (lo - n_halo)], self._peer(o), self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
 
     def _peer(self, rank_in_group: int) -> int:
         return rank_in_group if self.group is None else dist.get_global_rank(self.group, rank_in_group)
 
-    def combine(self, out: torch.Tensor, plan: tp.Optional[tp.Tuple[int, int, int]] = None) -> None:
-        """Assemble the stems on every rank.  ``out`` [rows, L] holds this rank's sample ranges and zeros elsewhere.
+    def _comm_device(self, like: torch.Tensor) -> torch.device:
+        return like.device if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
 
-        ``plan`` = (nseg, stride, length) when every pass used the same segment plan with no shift: rank q then
-        owns exactly the samples [lo_q*stride, hi_q*stride) (the last rank up to ``length``), so the pieces are
-        exchanged with ONE all-gather of compact [rows, max_len] buffers -- each rank receives (world-1)/world of
-        the result once, half the traffic of the general path.  Otherwise (shift trick: the owned ranges move
-        with the random offset of every pass) the zero-padded pieces are summed with an all-reduce.  Both give
-        the bit pattern of a single-GPU run."""
+    def agree(self, values: tp.List[int]) -> tp.List[int]:
+        """Rank 0's integers on every rank (the random shift offsets of apply.py:245: ranks that drew their own
+        would cut different windows)."""
         if self.world == 1:
-            return
-        if plan is None:
-            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
-            return
-        nseg, stride, length = plan
-        ranges = []
-        for q in range(self.world):
+            return list(values)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" \
+            else torch.device("cpu")
+        t = torch.tensor(list(values), dtype=torch.int64, device=dev)
+        dist.broadcast(t, src=self._peer(0), group=self.group)
+        return [int(v) for v in t.tolist()]
+
+    # ---- data-path exchange -------------------------------------------------------------------
+    def exchange_heads(self, segs: torch.Tensor, lo: int, hi: int, nseg: int, seg_len: int, stride: int, valid: int,
+                       length: int) -> tp.Optional[tp.Callable[[], None]]:
+        """segs [slots, rows, valid] = [own block [lo, hi) | halo slots for segments hi, hi+1, ...].
+
+        Sends the heads of this rank's first segments to the ranks on the left whose samples they reach, and posts
+        the receives for the heads of the segments right of ``hi``.  Every rank derives the same schedule.  Returns a
+        function that waits for the transfers and drops the received heads into the halo slots (None: nothing to do).
+        """
+        if self.world == 1:
+            return None
+        from .apply import owned_window
+        blocks = [self.block_of(r, nseg) for r in range(self.world)]
+        halo = self.halo(seg_len, stride)
+
+        def owner(g):
+            return next(q for q, (ql, qh) in enumerate(blocks) if ql <= g < qh)
+
+        ops, keep, unpack = [], [], []
+        for r, (l, h) in enumerate(blocks):
+            if h == l:
+                continue                                # empty block: owns no samples, needs no heads
+            w1 = owned_window(l, h, nseg, seg_len, stride, length)[1]
+            for g in range(h, min(h + halo, nseg)):     # the head of segment g reaches rank r's samples
+                n_g = min(length - g * stride, seg_len)
+                lead = (valid - n_g) // 2               # centre trim (utils.py:52-53)
+                width = min(n_g, w1 - g * stride)
+                if width <= 0:
+                    continue
+                o = owner(g)
+                if o == self.rank:
+                    buf = segs[g - lo][:, lead:lead + width].contiguous()
+                    keep.append(buf)
+                    ops.append(dist.P2POp(dist.isend, buf, self._peer(r), self.group))
+                elif r == self.rank:
+                    buf = torch.empty(segs.shape[1], width, dtype=segs.dtype, device=segs.device)
+                    unpack.append(((h - l) + (g - h), lead, width, buf))
+                    ops.append(dist.P2POp(dist.irecv, buf, self._peer(o), self.group))
+        if not ops:
+            return None
+        reqs = dist.batch_isend_irecv(ops)
+
+        def finish():
+            for req in reqs:
+                req.wait()
+            for slot, lead, width, buf in unpack:
+                segs[slot][:, lead:lead + width].copy_(buf)
+            keep.clear()
+        return finish
+
+    def combine(self, out: torch.Tensor, passes: tp.List[tp.Tuple[int, int, int, int, int]]) -> tp.Tuple[int, int]:
+        """``out`` [rows, L] holds what this rank overlap-added in every pass; ``passes`` lists each pass's
+        (nseg, seg_len, stride, window length, out_shift), from which every rank derives every rank's sample ranges.
+        Ownership = the ranges of the first pass (they tile [0, L)); contributions a later pass wrote outside them are
+        sent to their owners and added.  Then the ``gather`` policy.  Returns the range of ``out`` that is valid here.
+        """
+        from .apply import owned_window
+        L = out.shape[-1]
+        if self.world == 1:
+            self.owned = (0, L)
+            return self.owned
+
+        def rng(q, p):
+            nseg, seg_len, stride, length, out_shift = p
             lo, hi = self.block_of(q, nseg)
-            ranges.append((lo * stride, lo * stride) if hi == lo else
-                          (lo * stride, length if hi >= nseg else hi * stride))
-        width = max(b - a for a, b in ranges)
+            w0, w1 = owned_window(lo, hi, nseg, seg_len, stride, length)
+            return min(max(w0 - out_shift, 0), L), min(max(w1 - out_shift, 0), L)
+
+        own = [rng(q, passes[0]) for q in range(self.world)]
+        # pieces (sender q -> owner r, [a, b)) of the later passes that landed outside the sender's own range
+        sched = []
+        for q in range(self.world):
+            lo_q = min(rng(q, p)[0] for p in passes if rng(q, p)[1] > rng(q, p)[0]) if any(
+                rng(q, p)[1] > rng(q, p)[0] for p in passes) else own[q][0]
+            hi_q = max((rng(q, p)[1] for p in passes if rng(q, p)[1] > rng(q, p)[0]), default=own[q][1])
+            for a, b in ((lo_q, min(own[q][0], hi_q)), (max(own[q][1], lo_q), hi_q)):
+                if own[q][1] <= own[q][0]:
+                    a, b = lo_q, hi_q                  # a rank that owns nothing gives everything away (once)
+                for r in range(self.world):
+                    if r == q:
+                        continue
+                    x, y = max(a, own[r][0]), min(b, own[r][1])
+                    if y > x and (q, r, x, y) not in sched:
+                        sched.append((q, r, x, y))
+        ops, keep, adds = [], [], []
+        for q, r, x, y in sched:
+            if q == self.rank:
+                buf = out[:, x:y].contiguous()
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, self._peer(r), self.group))
+            elif r == self.rank:
+                buf = torch.empty(out.shape[0], y - x, dtype=out.dtype, device=out.device)
+                adds.append((x, y, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, self._peer(q), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            for x, y, buf in adds:
+                out[:, x:y] += buf
+        a, b = own[self.rank]
+        self.owned = (a, b)
+        if self.gather == "none":
+            return self.owned
         rows = out.shape[0]
-        a, b = ranges[self.rank]
-        local = torch.zeros(rows, width, dtype=out.dtype, device=out.device)
-        local[:, :b - a].copy_(out[:, a:b])
-        gathered = torch.empty(self.world * rows, width, dtype=out.dtype, device=out.device)   # rank-major
-        dist.all_gather_into_tensor(gathered, local, group=self.group)
-        for q, (a, b) in enumerate(ranges):
-            if q != self.rank and b > a:
-                out[:, a:b].copy_(gathered[q * rows:(q + 1) * rows, :b - a])
+        if self.gather == "all":
+            width = max(y - x for x, y in own)
+            local = torch.empty(rows, width, dtype=out.dtype, device=out.device)
+            local[:, :b - a].copy_(out[:, a:b])
+            gathered = torch.empty(self.world * rows, width, dtype=out.dtype, device=out.device)   # rank-major
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
+            for q, (x, y) in enumerate(own):
+                if q != self.rank and y > x:
+                    out[:, x:y].copy_(gathered[q * rows:(q + 1) * rows, :y - x])
+            self.owned = (0, L)
+            return self.owned
+        # "root": the pieces travel to rank 0 only
+        ops, recvs, keep = [], [], []
+        for q, (x, y) in enumerate(own):
+            if q == 0 or y <= x:
+                continue
+            if self.rank == q:
+                buf = out[:, x:y].contiguous()
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, self._peer(0), self.group))
+            elif self.rank == 0:
+                buf = torch.empty(rows, y - x, dtype=out.dtype, device=out.device)
+                recvs.append((x, y, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, self._peer(q), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            for x, y, buf in recvs:
+                out[:, x:y].copy_(buf)
+        if self.rank == 0:
+            self.owned = (0, L)
+        return self.owned

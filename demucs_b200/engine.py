@@ -191,6 +191,10 @@ class Engine:
         tw = np.stack([np.cos(2 * np.pi * k / cfg.nfft), -np.sin(2 * np.pi * k / cfg.nfft)], axis=1)
         self.twiddle = torch.from_numpy(tw.astype(np.float32)).to(self.device).contiguous()
         self.single_pass = mode in ("tf32", "bf16")      # reduced-precision modes: single-pass mma.sync thin-layer kernels
+        # arithmetic of the register-level (mma.sync) thin-layer kernels: single pass, or hi/lo split operands with
+        # three products in the strict tensor-core modes; the fp32 mode does not use them
+        self.thin_math = {"tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16, "tf32x3": _lib.MATH_TF32X3,
+                          "strict": _lib.MATH_BF16X3}.get(mode)
         self._w16_cache: tp.Dict[tp.Tuple, tp.Tuple[torch.Tensor, torch.Tensor]] = {}
         self._bufs: tp.Dict[tp.Tuple, tp.Dict[str, torch.Tensor]] = {}
         self._pos: tp.Dict[tp.Tuple, torch.Tensor] = {}
@@ -300,7 +304,7 @@ class Engine:
         slabs = B * Fr
         stat = (T * Fr, Fr, Fr)                      # slab(m) = b*Fr + fr
         tc = self.mode != "fp32"
-        narrow = self.single_pass and hid == 6 and C_ == 48     # dedicated mma.sync conv3, h stored 8 wide
+        narrow = tc and hid == 6 and C_ == 48     # dedicated mma.sync conv3, h stored 8 wide
         hp = 8 if narrow else ((hid + 15) // 16 * 16 if tc else hid)   # tensor-core arm: h is 16-column padded
         h = self._buf(key, f"dconv_h{tag}", M * hp)
         sums = self._buf(key, f"dconv_sums{tag}", 2 * slabs, torch.float64, zero=True)   # finalize clears it again
@@ -313,7 +317,7 @@ class Engine:
             # (1) h = conv3_dilated(x) and the GroupNorm statistics of h
             if narrow:
                 self._k("bd_dconv_conv3", ptr(x), ptr(W[f"{p}.w1"]), ptr(W[f"{p}.b1"]), ptr(h), hp, ptr(sums), M, C_, hid,
-                        T * Fr, Fr, dil, self._stream(), flops=2.0 * M * hid * 3 * C_, nbytes=4.0 * M * (C_ + hid),
+                        T * Fr, Fr, dil, self.thin_math, self._stream(), flops=2.0 * M * hid * 3 * C_, nbytes=4.0 * M * (C_ + hid),
                         label="dconv_conv3_mma", detail=f"M={M} C={C_} hid={hid} dil={dil}")
             elif Fr == 1:   # time branch: positions are the fast axis, one GroupNorm item per batch item
                 geo = dict(taps=((0, -dil), (0, 0), (0, dil)), I1=1, I0=T, J1=1, J0=T,
@@ -348,7 +352,7 @@ class Engine:
             self._k("bd_dconv_expand_update", ptr(h), hp, hid, ptr(mr1), ptr(W[f"{p}.g1"]), ptr(W[f"{p}.be1"]),
                     ptr(W[f"{p}.w2t"]), ptr(W[f"{p}.b2"]), ptr(mr2), ptr(W[f"{p}.g2"]), ptr(W[f"{p}.be2"]),
                     ptr(W[f"{p}.scale"]), ptr(x), M, C_, T * Fr, Fr,
-                    _lib.MATH_TF32 if self.single_pass else _lib.MATH_FP32, self._stream(),
+                    self.thin_math if tc else _lib.MATH_FP32, self._stream(),
                     nbytes=4.0 * M * (hid + 2 * C_), flops=4.0 * M * hid * C_, label="dconv_expand_update",
                     detail=f"M={M} C={C_} hid={hid}")
 
@@ -485,10 +489,10 @@ class Engine:
             y = self._buf(key, "y_t", B * Tout * Cc)
             first = i == 0
             Tin_p = Tin if first else tp(Tin)
-            conv0 = first and self.single_pass and Cc == 48 and A == 2     # dedicated mma.sync first-layer kernel
+            conv0 = first and self.mode != "fp32" and Cc == 48 and A == 2     # dedicated mma.sync first-layer kernel
             if conv0:
                 self._k("bd_encoder_conv0", ptr(xt), 1, norm.data_ptr() + 16, 8, ptr(W[f"tencoder.{i}.conv.w"]),
-                        ptr(W[f"tencoder.{i}.conv.b"]), ptr(y), B, 1, Tout, L, A, Cc, self._stream(),
+                        ptr(W[f"tencoder.{i}.conv.b"]), ptr(y), B, 1, Tout, L, A, Cc, self.thin_math, self._stream(),
                         flops=2.0 * B * Tout * Cc * 8 * A, nbytes=4.0 * B * (A * L + Tout * Cc), label="encoder_conv0_mma",
                         detail=f"M={B * Tout} cin={A}")
             else:
@@ -512,7 +516,7 @@ class Engine:
             y = self._buf(key, "y_f", B * T * Fo * Cc)
             if conv0 and Cin == 4:
                 self._k("bd_encoder_conv0", ptr(xf), 0, ptr(norm), 8, ptr(W[f"encoder.{i}.conv.w"]),
-                        ptr(W[f"encoder.{i}.conv.b"]), ptr(y), B, T, Fo, Fin, Cin, Cc, self._stream(),
+                        ptr(W[f"encoder.{i}.conv.b"]), ptr(y), B, T, Fo, Fin, Cin, Cc, self.thin_math, self._stream(),
                         flops=2.0 * B * T * Fo * Cc * 8 * Cin, nbytes=4.0 * B * T * (Fin * Cin + Fo * Cc),
                         label="encoder_conv0_mma", detail=f"M={B * T * Fo} cin={Cin}")
             else:

@@ -136,23 +136,26 @@ int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float*
  *          gram_ws: optional workspace of (slabs + 1) * (hid*hid + hid) + hid + 2 doubles, ALL ZERO on entry (it is
  *          returned all zero in its first slabs*(hid*hid+hid) entries).  When given (hid in 6/12/24/48) the sums are
  *          derived from the slab's Gram matrix sum(g g^T): hid^2 instead of hid*2C products per row.
- * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place); math = BD_MATH_*: the
- *          BD_MATH_TF32 runs the expansion on mma.sync tf32 fragments, the other modes in exact fp32 */
+ * _update: x[m, c] += scale[c] * gn2(u)[2c] * sigmoid(gn2(u)[2c+1])            (in place); math = BD_MATH_*:
+ *          BD_MATH_TF32 / BD_MATH_BF16 run the expansion on mma.sync tf32 fragments, BD_MATH_TF32X3 / BD_MATH_BF16X3 on
+ *          the same fragments with hi/lo split operands (three products), BD_MATH_FP32 in exact fp32 */
 /* First encoder layer of a branch (hdemucs.py:110,139-144): out = gelu(conv_{k=8,s=4,p=2}((x - mean_b) * rstd_b) + bias)
  * with the per-item input normalisation (htdemucs.py:545-554) folded into the load; positions outside [0, Jin) are
  * zero AFTER normalisation.  mean_b = norm[b*norm_stride], rstd_b = norm[b*norm_stride + 2] (bd_finalize_item_norm).
  *   channel_major = 0: x [B, I1, Jin, cin] channels-last (spectrogram, cin = 4);  = 1: x [B, cin, Jin] (the mix, cin = 2,
- *   I1 = 1).  w [cout, 8*cin] tap-major, out [B, I1, Io, cout].  mma.sync tf32 fragments (BD_MATH_TF32 class);
- *   only cout = 48 is built. */
+ *   I1 = 1).  w [cout, 8*cin] tap-major, out [B, I1, Io, cout].  mma.sync tf32 fragments: single pass for
+ *   math = BD_MATH_TF32 / BD_MATH_BF16, hi/lo split operands and three products (fp32-class) for BD_MATH_TF32X3 /
+ *   BD_MATH_BF16X3; only cout = 48 is built. */
 int bd_encoder_conv0(const float* x, int channel_major, const float* norm, int norm_stride, const float* w, const float* bias,
-                     float* out, int B, int I1, int Io, int Jin, int cin, int cout, void* stream);
+                     float* out, int B, int I1, int Io, int Jin, int cin, int cout, int math, void* stream);
 /* DConv dilated k=3 convolution of a narrow layer (demucs.py:138, hid = C/8 = 6) with its GroupNorm statistics,
  * on mma.sync tf32 fragments (BD_MATH_TF32 class arithmetic).  x [M, C] rows in memory order, the conv axis is
  * the position t = (m % rows_per_item) / slabs_per_item, neighbours are dilation * slabs_per_item rows away and
  * read as zero outside the item.  w1 [hid, 3*C] tap-major, h [M, ldh = 8] (columns hid.. are written as zero),
- * sums1[slab] += (sum, sumsq) of h; slab map as bd_dconv_tail.  Only hid 6 / C 48 is built. */
+ * sums1[slab] += (sum, sumsq) of h; slab map as bd_dconv_tail.  Only hid 6 / C 48 is built.  math as for
+ * bd_encoder_conv0. */
 int bd_dconv_conv3(const float* x, const float* w1, const float* b1, float* h, int ldh, double* sums1, long long M, int C,
-                   int hid, long long rows_per_item, int slabs_per_item, int dilation, void* stream);
+                   int hid, long long rows_per_item, int slabs_per_item, int dilation, int math, void* stream);
 int bd_dconv_expand_stats(const float* h, int ldh, int hid, const float* mean_rstd1, const float* gamma1,
                           const float* beta1, const float* w2t, const float* b2, double* sums2, double* gram_ws,
                           long long M, int C, long long rows_per_item, int slabs_per_item, void* stream);
@@ -194,6 +197,13 @@ int bd_overlap_add(const float* segs, const float* weight, float* out, int seg_f
                    int rows, int valid, int seg_len, int stride, long long length, long long out_ld,
                    long long out_shift, long long n_begin, long long n_end, const float* row_alpha, float alpha,
                    int accumulate, void* stream);
+
+/* Input side of the batcher (apply.py:108-124,278-284: TensorChunk(...).padded(valid) of every segment):
+ * batch[(j*B + b), c, :] = the `valid` samples centred on segment seg_first + j of the window [offset0,
+ * offset0 + length) of track [B, C, track_len]; real signal where the track has it, zeros beyond its ends. */
+int bd_gather_segments(const float* track, float* batch, int B, int C, long long track_len, long long offset0,
+                       long long length, int seg_first, int nseg_batch, int seg_len, int stride, int valid,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -206,7 +206,7 @@ def _dconv_u(h, ldh, hid, mr1, g1, be1, w2t, b2, M, Cc, rpi, spi):
     return u.astype(np.float32), slab
 
 
-def bd_encoder_conv0(x, channel_major, norm, norm_stride, w, bias, out, B, I1, Io, Jin, cin, cout, stream):
+def bd_encoder_conv0(x, channel_major, norm, norm_stride, w, bias, out, B, I1, Io, Jin, cin, cout, math, stream):
     nv = f32(norm, (B - 1) * norm_stride + 3)
     wv = f32(w, cout * 8 * cin).reshape(cout, 8, cin)
     ov = f32(out, B * I1 * Io * cout).reshape(B, I1, Io, cout)
@@ -225,7 +225,7 @@ def bd_encoder_conv0(x, channel_major, norm, norm_stride, w, bias, out, B, I1, I
         ov[b] = gelu(acc)
 
 
-def bd_dconv_conv3(x, w1, b1, h, ldh, sums1, M, Cc, hid, rpi, spi, dil, stream):
+def bd_dconv_conv3(x, w1, b1, h, ldh, sums1, M, Cc, hid, rpi, spi, dil, math, stream):
     xv = f32(x, M * Cc).reshape(M, Cc)
     w = f32(w1, hid * 3 * Cc).reshape(hid, 3, Cc)
     m = np.arange(M)
@@ -336,6 +336,19 @@ def bd_overlap_add(segs, weight, out, seg_first, nseg_local, nseg, rows, valid, 
         ov[:, n_begin - out_shift:] += res
     else:
         ov[:, n_begin - out_shift:] = res
+
+
+def bd_gather_segments(track, batch, B, Cc, track_len, offset0, length, seg_first, nseg_batch, seg_len, stride, valid, stream):
+    tr = f32(track, B * Cc * track_len).reshape(B * Cc, track_len)
+    out = f32(batch, nseg_batch * B * Cc * valid).reshape(nseg_batch, B * Cc, valid)
+    for j in range(nseg_batch):
+        i = seg_first + j
+        n_i = min(length - i * stride, seg_len)
+        start = offset0 + i * stride - (valid - n_i) // 2
+        lo, hi = max(0, start), min(track_len, start + valid)
+        out[j] = 0
+        if hi > lo:
+            out[j][:, lo - start:hi - start] = tr[:, lo:hi]
 
 
 TABLE = {k: v for k, v in globals().items() if k.startswith("bd_")}

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, kwargs, length, ret):
+def _worker(rank, world, port, kwargs, length, ret, gather="all"):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -28,9 +28,13 @@ def _worker(rank, world, port, kwargs, length, ret):
     model = D.HTDemucs.from_config(cfg, init_seed=0, layer_scale=0.5)
     mix = synth_mix(1, length, 3)
     with emulated_abi():
-        random.seed(7)
-        out = D.apply_model(model, mix, shard=Shard(), **kwargs)
-    if rank == 0:
+        random.seed(7 + 1000 * rank)       # ranks draw DIFFERENT shift offsets: rank 0's must win on all of them
+        shard = Shard(gather=gather)
+        out = D.apply_model(model, mix, shard=shard, **kwargs)
+    if gather == "none":                    # every rank reports the range it owns
+        a, b = shard.owned
+        ret.put((rank, a, b, out[..., a:b].numpy()))
+    elif rank == 0:
         ret.put(out.numpy())
     dist.barrier()
     dist.destroy_process_group()
@@ -67,6 +71,31 @@ def test_sharded_apply_matches_single_process(kwargs, length):
     want = _single(kwargs, length)
     assert got.shape == want.shape
     assert abs(got - want).max() <= 1e-6 * abs(want).max()
+
+
+@pytest.mark.parametrize("gather", ["none", "root"])
+def test_sharded_apply_gather_policies(gather):
+    """gather="none": the ranks' owned ranges tile the track and hold the single-process values (shifts=2: the
+    ranges of the two passes differ, the slivers travel to their owners); gather="root": rank 0 has everything."""
+    kwargs, length = dict(shifts=2, overlap=0.25), 150000
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = 29500 + random.randrange(2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, kwargs, length, ret, gather)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [ret.get() for _ in range(2 if gather == "none" else 1)]
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    want = _single(kwargs, length)
+    if gather == "root":
+        assert abs(got[0] - want).max() <= 1e-6 * abs(want).max()
+        return
+    got.sort(key=lambda t: t[0])
+    assert got[0][1] == 0 and got[0][2] == got[1][1] and got[1][2] == length
+    for _, a, b, piece in got:
+        assert abs(piece - want[..., a:b]).max() <= 1e-6 * abs(want).max()
 
 
 def test_block_partition_and_halo():

@@ -40,7 +40,7 @@ def test_apply_model_and_bag_match_reference_golden():
     mix = synth_mix(1, int(g["length"]), 99)
     stride = int(g["stride"])
     with emulated_abi():
-        for name in ("power2", "nosplit"):   # shifts + RNG stream + transition power; leaf branch
+        for name in ("power2", "nosplit", "shifts2"):   # shifts + RNG stream + transition power; leaf branch; two shifts
             m = mix[..., :50000] if name == "nosplit" else mix
             random.seed(0)
             out = D.apply_model(models[0], m.clone(), **APPLY_CASES[name])
@@ -104,7 +104,7 @@ def test_emulated_dconv_conv3_is_the_dilated_conv():
     M = B * T * Fr
     h = torch.zeros(M, 8)
     sums = torch.zeros(B * Fr, 2, dtype=torch.float64)
-    E.bd_dconv_conv3(x.data_ptr(), w1.data_ptr(), b.data_ptr(), h.data_ptr(), 8, sums.data_ptr(), M, C, hid, T * Fr, Fr, dil, 0)
+    E.bd_dconv_conv3(x.data_ptr(), w1.data_ptr(), b.data_ptr(), h.data_ptr(), 8, sums.data_ptr(), M, C, hid, T * Fr, Fr, dil, 1, 0)
     want = torch.nn.functional.conv1d(x.permute(0, 2, 3, 1).reshape(B * Fr, C, T), w, b, padding=dil, dilation=dil)
     rows = want.reshape(B, Fr, hid, T).permute(0, 3, 1, 2).reshape(M, hid)
     assert rel_l2(h[:, :hid], rows) < 1e-5
@@ -129,7 +129,7 @@ def test_emulated_encoder_conv0(channel_major):
     wp = w.permute(0, 2, 1).reshape(cout, 8 * cin).contiguous()
     out = torch.zeros(B, I1, Io, cout)
     E.bd_encoder_conv0(x.data_ptr(), channel_major, norm.data_ptr(), 8, wp.data_ptr(), b.data_ptr(), out.data_ptr(),
-                       B, I1, Io, Jin, cin, cout, 0)
+                       B, I1, Io, Jin, cin, cout, 1, 0)
     xn = F.pad((xin - 0.3) * 1.7, (2, 4 * Io + 6 - Jin))
     want = F.gelu(F.conv1d(xn, w, b, stride=4))[..., :Io].reshape(B, I1, cout, Io).permute(0, 1, 3, 2)
     assert rel_l2(out, want) < 1e-5
