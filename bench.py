@@ -265,10 +265,9 @@ def gpu_arm(args) -> None:
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    a, b = last["own"]
-    lo_seg, hi_seg = shard.block(nseg) if shard is not None else (0, nseg)
-    in_lo, in_hi = lo_seg * STRIDE, min(length, (hi_seg - 1) * STRIDE + SEG_LEN) if hi_seg > lo_seg else lo_seg * STRIDE
-    io = torch.tensor([2.0 * (in_hi - in_lo) * 4, 8.0 * (b - a) * 4], dtype=torch.float64, device=dev)
+    from demucs_b200 import apply as _apply
+    io = torch.tensor([float(_apply.LAST_IO["h2d_bytes"]), float(_apply.LAST_IO["d2h_bytes"])], dtype=torch.float64,
+                      device=dev)      # counted by apply_model from the tensors it copied
     if world > 1:
         dist.all_reduce(io)
         dist.all_reduce(launches)

@@ -46,7 +46,7 @@ class GemmDesc(C.Structure):
         ("out", C.c_void_p), ("os_b", C.c_longlong), ("os_1", C.c_longlong), ("os_0", C.c_longlong),
         ("convt", C.c_int), ("O0", C.c_int), ("oc_split", C.c_int), ("oc_stride", C.c_longlong),
         ("stats_out", C.c_void_p), ("stat_div", C.c_int), ("stat_mul", C.c_int), ("stat_mod", C.c_int),
-        ("math", C.c_int), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p),
+        ("math", C.c_int), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p), ("x_bf16", C.c_int), ("out_bf16", C.c_int),
     ]
 
 
@@ -66,7 +66,8 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_dconv_expand_stats": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
     "bd_dconv_expand_update": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _I, _P],
     "bd_gn_gelu_apply": [_P, _P, _P, _P, _LL, _I, _LL, _I, _P],
-    "bd_layer_norm": [_P, _P, _P, _P, _P, _I, _LL, _I, _P],
+    "bd_layer_norm": [_P, _P, _P, _P, _P, _I, _LL, _I, _I, _P],
+    "bd_attention_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bd_item_stats": [_P, _P, _I, _LL, _P],
     "bd_group_norm_apply": [_P, _P, _P, _P, _I, _LL, _I, _P],
     "bd_attention_workspace": [_I, _I, _I, _I, _I],

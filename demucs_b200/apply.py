@@ -283,6 +283,9 @@ def _overlap_add(eng, segs, weight, out, seg_first, nseg_local, nseg, rows, vali
            eng._stream(), nbytes=4.0 * rows * (n_end - n_begin) * (2 + (1 if accumulate else 0)))
 
 
+LAST_IO = {"h2d_bytes": 0, "d2h_bytes": 0}     # host <-> device bytes of the last apply_model call on host buffers
+
+
 class _HostSink:
     """Streams finished output ranges to a pinned host tensor on a side stream while later segments compute."""
 
@@ -347,7 +350,21 @@ def apply_model(model: tp.Union[BagOfModels, Model],
     guard = torch.cuda.device(device) if on_cuda else contextlib.nullcontext()
     with guard:
         to_host = on_cuda and mix.device.type == "cpu"
-        track = mix.to(device=device, dtype=torch.float32, non_blocking=to_host and mix.is_pinned())   # one H2D
+        if to_host and shard is not None and not shifts and mix.dtype == torch.float32:
+            # a rank uploads only the stretch of the track its own segments read (centre padding included)
+            valid, seg_len, stride, offsets = _segment_plan(models[0], length, split, overlap, segment)
+            lo_seg, hi_seg = shard.block(len(offsets))
+            starts = [i * stride - (valid - min(length - i * stride, seg_len)) // 2 for i in range(lo_seg, hi_seg)]
+            lo = max(0, min(starts, default=0))
+            hi = min(length, max(starts, default=0) + valid) if starts else 0
+            track = torch.empty(batch, channels, length, dtype=torch.float32, device=device)
+            for b_ in range(batch if hi > lo else 0):
+                for c_ in range(channels):     # contiguous pinned run -> contiguous device run
+                    track[b_, c_, lo:hi].copy_(mix[b_, c_, lo:hi], non_blocking=mix.is_pinned())
+            h2d_bytes = batch * channels * max(hi - lo, 0) * 4
+        else:
+            track = mix.to(device=device, dtype=torch.float32, non_blocking=to_host and mix.is_pinned())   # one H2D
+            h2d_bytes = mix.numel() * 4 if to_host else 0
         n_passes = len(models) * max(shifts, 1)
         # every pass but the first accumulates; a sharded multi-pass run also accumulates into ranges its first pass
         # did not write (the owned ranges move with the shift), so only that case needs a zero fill
@@ -416,4 +433,5 @@ def apply_model(model: tp.Union[BagOfModels, Model],
         if sink is None:
             sink = _HostSink(out, device)
             sink(*own)
+        LAST_IO["h2d_bytes"], LAST_IO["d2h_bytes"] = h2d_bytes, sink.bytes
         return sink.finish().view(batch, S, channels, length)

@@ -50,6 +50,10 @@ int bd_conv_gemm(const bd_gemm_desc* d, void* stream) {
     int rc = bd_conv_gemm_tc(d, stream, &handled);
     if (rc != BD_OK || handled) return rc;
   }
+  if (d->x_bf16 || d->out_bf16) {
+    bd_set_error("bd_conv_gemm: bf16 tensors need the tensor-core arm (BD_MATH_BF16, Cin %% 64 == 0, N >= 16, M >= 128)");
+    return BD_ERR_ARG;
+  }
   return bd_conv_gemm_simt(d, stream);
 }
 

@@ -149,12 +149,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return r;
 }
 
-template <bool X3>
+template <bool X3, bool O16>
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_b16_kernel(
     const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_q_lo,
     const __grid_constant__ CUtensorMap map_k_lo, const __grid_constant__ CUtensorMap map_v_lo,
-    float* __restrict__ o, int Tq, int Tk, int ldo) {
+    void* __restrict__ ov, int Tq, int Tk, int ldo) {
   using C_ = BCfg<X3>;
   constexpr int NP = C_::NP, NS = C_::NS;
   constexpr int kQBytes = C_::kQBytes, kKBytes = C_::kKBytes, kVBytes = C_::kVBytes;
@@ -409,12 +409,25 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_b16_kernel(
     const float a_s = w_s * inv, a_o = w_o * inv;
     const int r = q0 + row;
     if (r < Tq) {
-      float4* dst = reinterpret_cast<float4*>(o + ((size_t)b * Tq + r) * ldo + h * HD + 32 * g);
+      const size_t at = ((size_t)b * Tq + r) * ldo + h * HD + 32 * g;
+      if (O16) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ov) + at);
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(theirs + c);
-        dst[c >> 2] = make_float4(fmaf(own[c], a_s, t.x * a_o), fmaf(own[c + 1], a_s, t.y * a_o),
-                                  fmaf(own[c + 2], a_s, t.z * a_o), fmaf(own[c + 3], a_s, t.w * a_o));
+        for (int c = 0; c < 32; c += 8) {
+          const float4 t0 = *reinterpret_cast<const float4*>(theirs + c), t1 = *reinterpret_cast<const float4*>(theirs + c + 4);
+          dst[c >> 3] = make_uint4(pack_bf16(fmaf(own[c], a_s, t0.x * a_o), fmaf(own[c + 1], a_s, t0.y * a_o)),
+                                   pack_bf16(fmaf(own[c + 2], a_s, t0.z * a_o), fmaf(own[c + 3], a_s, t0.w * a_o)),
+                                   pack_bf16(fmaf(own[c + 4], a_s, t1.x * a_o), fmaf(own[c + 5], a_s, t1.y * a_o)),
+                                   pack_bf16(fmaf(own[c + 6], a_s, t1.z * a_o), fmaf(own[c + 7], a_s, t1.w * a_o)));
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ov) + at);
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(theirs + c);
+          dst[c >> 2] = make_float4(fmaf(own[c], a_s, t.x * a_o), fmaf(own[c + 1], a_s, t.y * a_o),
+                                    fmaf(own[c + 2], a_s, t.z * a_o), fmaf(own[c + 3], a_s, t.w * a_o));
+        }
       }
     }
   }
@@ -430,8 +443,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// dense bf16 [B, T, D] -> boxes of 128 rows x 64 columns, SWIZZLE_128B
-bool make_map_b16(CUtensorMap* map, const void* base, int D, int T, int B) {
+// bf16 [B, T, ld] (columns 0 .. D-1 from `base`) -> boxes of 128 rows x 64 columns, SWIZZLE_128B
+bool make_map_b16(CUtensorMap* map, const void* base, int D, int T, int B, int ld = 0) {
+  if (!ld) ld = D;
   static EncodeTiledFn enc = nullptr;
   if (!enc) {
     void* p = nullptr;
@@ -442,7 +456,7 @@ bool make_map_b16(CUtensorMap* map, const void* base, int D, int T, int B) {
     enc = (EncodeTiledFn)p;
   }
   cuuint64_t dim[3] = {(cuuint64_t)D, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t str[2] = {(cuuint64_t)D * 2, (cuuint64_t)T * D * 2};
+  cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
   cuuint32_t box[3] = {64, 128, 1};
   cuuint32_t es[3] = {1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -472,16 +486,16 @@ __global__ void split_rows_b16_kernel(const float* __restrict__ x, uint16_t* __r
   }
 }
 
-template <bool X3>
-int launch_attention_b16(const CUtensorMap* m, float* o, int B, int H, int Tq, int Tk, int ldo, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(attention_b16_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <bool X3, bool O16>
+int launch_attention_b16(const CUtensorMap* m, void* o, int B, int H, int Tq, int Tk, int ldo, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(attention_b16_kernel<X3, O16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        BCfg<X3>::kSmem);
   if (e != cudaSuccess) {
     bd_set_error("bd_attention_b16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return BD_ERR_CUDA;
   }
   dim3 grid((Tq + TQ - 1) / TQ, H, B);
-  attention_b16_kernel<X3><<<grid, AT_THREADS, BCfg<X3>::kSmem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], o, Tq, Tk, ldo);
+  attention_b16_kernel<X3, O16><<<grid, AT_THREADS, BCfg<X3>::kSmem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], o, Tq, Tk, ldo);
   return bd_check_launch("attention_b16_kernel");
 }
 
@@ -533,5 +547,24 @@ int bd_attention_b16(const float* q, const float* k, const float* v, float* o, i
     bd_set_error("bd_attention_b16: cuTensorMapEncodeTiled failed");
     return BD_ERR_CUDA;
   }
-  return x3 ? launch_attention_b16<true>(m, o, B, H, Tq, Tk, ldo, st) : launch_attention_b16<false>(m, o, B, H, Tq, Tk, ldo, st);
+  return x3 ? launch_attention_b16<true, false>(m, o, B, H, Tq, Tk, ldo, st)
+            : launch_attention_b16<false, false>(m, o, B, H, Tq, Tk, ldo, st);
+}
+
+// bf16 tensors in, bf16 out: no conversion pass, no workspace
+extern "C" int bd_attention_bf16(const void* q, const void* k, const void* v, void* o, int B, int H, int Tq, int Tk, int ldq,
+                                 int ldk, int ldv, int ldo, void* stream) {
+  BD_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "bd_attention_bf16: bad sizes");
+  BD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "bd_attention_bf16: leading dims must be multiples of 8");
+  BD_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) == 0, "bd_attention_bf16: unaligned tensor");
+  const int D = H * HD;
+  alignas(64) CUtensorMap m[6];
+  if (!(make_map_b16(&m[0], q, D, Tq, B, ldq) && make_map_b16(&m[1], k, D, Tk, B, ldk) && make_map_b16(&m[2], v, D, Tk, B, ldv))) {
+    bd_set_error("bd_attention_bf16: cuTensorMapEncodeTiled failed");
+    return BD_ERR_CUDA;
+  }
+  m[3] = m[0];
+  m[4] = m[1];
+  m[5] = m[2];
+  return launch_attention_b16<false, true>(m, o, B, H, Tq, Tk, ldo, (cudaStream_t)stream);
 }

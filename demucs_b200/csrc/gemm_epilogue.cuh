@@ -57,6 +57,31 @@ __device__ __forceinline__ long long bd_col_ofs(const bd_gemm_desc& d, int no) {
   return (long long)g * d.oc_stride + (no - g * d.oc_split);
 }
 
+// output stores: fp32, or bf16 (round to nearest even) when the descriptor says the output tensor is bf16
+__device__ __forceinline__ uint32_t bd_pack_bf16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void bd_store_out4(const bd_gemm_desc& d, long long o, float4 v) {
+  if (d.out_bf16)
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(d.out) + o) = make_uint2(bd_pack_bf16(v.x, v.y), bd_pack_bf16(v.z, v.w));
+  else
+    *reinterpret_cast<float4*>(d.out + o) = v;
+}
+__device__ __forceinline__ void bd_store_out2(const bd_gemm_desc& d, long long o, float2 v) {
+  if (d.out_bf16)
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(d.out) + o) = bd_pack_bf16(v.x, v.y);
+  else
+    *reinterpret_cast<float2*>(d.out + o) = v;
+}
+__device__ __forceinline__ void bd_store_out1(const bd_gemm_desc& d, long long o, float v) {
+  if (d.out_bf16)
+    reinterpret_cast<uint16_t*>(d.out)[o] = (uint16_t)(bd_pack_bf16(v, 0.f) & 0xffffu);
+  else
+    d.out[o] = v;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
@@ -154,7 +179,7 @@ __device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiR
       o2.x = fmaf(c.scale.x, o2.x, e.resid.x); o2.y = fmaf(c.scale.y, o2.y, e.resid.y);
     }
     o2.x += e.addend.x; o2.y += e.addend.y;
-    if (d.out) *reinterpret_cast<float2*>(d.out + e.o) = o2;
+    if (d.out) bd_store_out2(d, e.o, o2);
     s += o2.x + o2.y;
     q = fmaf(o2.x, o2.x, fmaf(o2.y, o2.y, q));
     return;
@@ -168,7 +193,7 @@ __device__ __forceinline__ void bd_epi_finish4(const bd_gemm_desc& d, const EpiR
     v.z = fmaf(c.scale.z, v.z, e.resid.z); v.w = fmaf(c.scale.w, v.w, e.resid.w);
   }
   v.x += e.addend.x; v.y += e.addend.y; v.z += e.addend.z; v.w += e.addend.w;
-  if (d.out) *reinterpret_cast<float4*>(d.out + e.o) = v;
+  if (d.out) bd_store_out4(d, e.o, v);
   s += (v.x + v.y) + (v.z + v.w);
   q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
 }
@@ -212,7 +237,7 @@ __device__ __forceinline__ bool bd_epi_apply(const bd_gemm_desc& d, const EpiRow
   if (d.rowbias) v += __ldg(d.rowbias + (size_t)r.rb_row * Nout + no);
   if (d.resid) v = fmaf(d.scale ? __ldg(d.scale + no) : 1.f, v, __ldg(d.resid + o));
   if (d.addend) v += __ldg(d.addend + o);
-  if (d.out) d.out[o] = v;
+  if (d.out) bd_store_out1(d, o, v);
   stored = v;
   return true;
 }

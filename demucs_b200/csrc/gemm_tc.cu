@@ -5,6 +5,7 @@
 
 int bd_tc_launch_bf16x3(int tbk, int tbn, const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st);
 int bd_tc_launch_bf16(int tbk, int tbn, const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st);
+int bd_tc_launch_bf16d(int tbk, int tbn, const bd_gemm_desc& d, const TileGeom& g, int items, cudaStream_t st);
 
 namespace {
 int pow2_ceil(int v) {
@@ -19,6 +20,10 @@ bool bd_conv_gemm_tc_eligible(const bd_gemm_desc& d) {
   if (d.a_mode != BD_A_NONE || d.xs_c != 1 || d.m1 != 1) return false;
   if (!(d.m0 == 1 || (d.m0 == 4 && d.J0 % 4 == 0))) return false;
   if (d.Cin % 16 != 0 || d.N < 16 || d.K < 16 || d.M < 128 || d.taps > BD_MAX_TAPS) return false;
+  if (d.x_bf16) {   // bf16 A tensor: TMA strides are multiples of 16 bytes = 8 elements, 64-element k-blocks
+    if (d.math != BD_MATH_BF16 || d.Cin % 64 != 0) return false;
+    if (d.xs_0 % 8 != 0 || (d.J1 > 1 && d.xs_1 % 8 != 0) || d.xs_b % 8 != 0) return false;
+  }
   if (d.xs_0 % 4 != 0 || (d.J1 > 1 && d.xs_1 % 4 != 0) || d.xs_b % 4 != 0) return false;
   if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15)) return false;
   if (d.math == BD_MATH_BF16X3 || d.math == BD_MATH_BF16) {   // pre-split bf16 weight planes [N, K]
@@ -69,6 +74,7 @@ int tile_width(const bd_gemm_desc& d, const TileGeom& g) {
 // multiple of 16; 3xTF32: 16 (hi/lo stages are twice the size); bf16 families: 32 whenever Cin allows (the fp32 stage
 // is split in place, so the stage does not grow).
 static int k_block(const bd_gemm_desc& d, int tbn) {
+  if (d.x_bf16) return 64;
   if (d.math == BD_MATH_BF16X3 || d.math == BD_MATH_BF16) return d.Cin % 32 == 0 ? 32 : 16;
   return (tbn == 256 || d.math == BD_MATH_TF32X3 || d.Cin % 32 != 0) ? 16 : 32;
 }
@@ -95,7 +101,9 @@ int bd_conv_gemm_tc(const bd_gemm_desc* dp, void* stream, int* handled) {
   int rc;
   switch (d.math) {
     case BD_MATH_BF16X3: rc = bd_tc_launch_bf16x3(tbk, tbn, d, g, items, st); break;
-    case BD_MATH_BF16: rc = bd_tc_launch_bf16(tbk, tbn, d, g, items, st); break;
+    case BD_MATH_BF16:
+      rc = d.x_bf16 ? bd_tc_launch_bf16d(tbk, tbn, d, g, items, st) : bd_tc_launch_bf16(tbk, tbn, d, g, items, st);
+      break;
     case BD_MATH_TF32X3:
       rc = tbn == 256 ? launch_tc_persist<16, 256, BD_TC_TF32X3>(d, g, items, st)
                       : launch_tc_width<16, BD_TC_TF32X3>(tbn, d, g, items, st);

@@ -43,12 +43,14 @@
 //                    16 mantissa bits per operand (rel. error ~4e-6 per layer) at 1.5x the cost of one tf32 pass:
 //                    the arithmetic of the default ("strict", <= 1e-4) mode
 //   MODE 3  BF16     kind::f16 (bf16), single product (the reduced-precision "bf16" mode)
+//   MODE 4  BF16D    the same with a bf16 A tensor in HBM: the tile arrives by TMA in operand form (64 elements =
+//                    128-byte rows per k-block), no splitter warps
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
 #include "gemm_epilogue.cuh"
 
-enum { BD_TC_TF32 = 0, BD_TC_TF32X3 = 1, BD_TC_BF16X3 = 2, BD_TC_BF16 = 3 };
+enum { BD_TC_TF32 = 0, BD_TC_TF32X3 = 1, BD_TC_BF16X3 = 2, BD_TC_BF16 = 3, BD_TC_BF16D = 4 };
 
 struct TileGeom {
   int R0, R1;            // tile = R1 rows (i1) x R0 positions (i0), R0 * R1 == 128, powers of two
@@ -204,7 +206,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc16(const void* smem, int sbo
   uint64_t desc = (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
   desc |= (uint64_t)(sbo >> 4) << 32;
   desc |= (uint64_t)1 << 46;
-  desc |= (uint64_t)(TBK == 32 ? 4 : 6) << 61;
+  desc |= (uint64_t)(TBK == 64 ? 2 : TBK == 32 ? 4 : 6) << 61;      // 128 / 64 / 32-byte rows
   return desc;
 }
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -304,7 +306,7 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
     colofs = (long long)rr * d.os_0 + (nc - rr * cout);
     rr -= d.convt == 1 ? 2 : 0;
   }
-  float* outp = d.out + colofs;
+  const long long outo = colofs;
   const float* resp = RES ? d.resid + colofs : nullptr;
   const float* addp = CT && d.addend ? d.addend + colofs : nullptr;
   const float* rbp = ROWB ? d.rowbias + no : nullptr;
@@ -369,7 +371,7 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
           o2.y = fmaf(scl.y, o2.y, res[u].y);
         }
         if (ok[u]) {
-          *reinterpret_cast<float2*>(outp + ob[u]) = o2;
+          bd_store_out2(d, outo + ob[u], o2);
           ssum += o2.x + o2.y;
           ssq = fmaf(o2.x, o2.x, fmaf(o2.y, o2.y, ssq));
         }
@@ -385,7 +387,7 @@ __device__ __forceinline__ void epi_fast_rows(const bd_gemm_desc& d, uint32_t st
           v.x += res[u].x; v.y += res[u].y; v.z += res[u].z; v.w += res[u].w;
         }
         if (ok[u]) {
-          *reinterpret_cast<float4*>(outp + ob[u]) = v;
+          bd_store_out4(d, outo + ob[u], v);
           ssum += (v.x + v.y) + (v.z + v.w);
           ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
         }
@@ -421,8 +423,9 @@ __device__ __forceinline__ int epi_fast_id(const bd_gemm_desc& d, bool vec, bool
 template <int TBK, int TBN, int MODE>
 struct PCfg {
   static constexpr bool kX3 = MODE == BD_TC_TF32X3;                          // fp32 hi / lo tiles side by side
-  static constexpr bool kB16 = MODE == BD_TC_BF16X3 || MODE == BD_TC_BF16;   // bf16 operands
-  static constexpr bool kSplit = MODE != BD_TC_TF32;                         // splitter warps present
+  static constexpr bool kB16 = MODE == BD_TC_BF16X3 || MODE == BD_TC_BF16 || MODE == BD_TC_BF16D;   // bf16 operands
+  static constexpr bool kDirect = MODE == BD_TC_BF16D;                       // A is bf16 in HBM
+  static constexpr bool kSplit = MODE != BD_TC_TF32 && !kDirect;             // splitter warps present
   static constexpr int kBParts = MODE == BD_TC_BF16X3 ? 2 : 1;               // bf16 weight planes per stage (hi, lo)
   static constexpr int kPGroups = (MODE == BD_TC_TF32X3 || MODE == BD_TC_BF16X3) ? 2 : BD_TC_EPI_GROUPS;
   // warps: 0 TMA, 1 MMA, then the splitters (3xTF32: warps 4..7; bf16x3: warps 2..5; bf16: warps 2..3 -- one
@@ -431,7 +434,7 @@ struct PCfg {
   static constexpr int kSplitWarps = MODE == BD_TC_BF16 ? 2 : 4;
   static constexpr int kEpiWarp0 = kSplit ? kSplitWarp0 + kSplitWarps : 4;
   static constexpr int kThreads = 32 * kEpiWarp0 + 128 * kPGroups;
-  static constexpr int kTileBytesA = TBM * TBK * 4;                          // fp32 from TMA (bf16 modes: split in place)
+  static constexpr int kTileBytesA = TBM * TBK * (kDirect ? 2 : 4);          // fp32 from TMA (bf16 modes: split in place)
   static constexpr int kTileBytesB = kB16 ? TBN * TBK * 2 : TBN * TBK * 4;
   static constexpr int kStageBytesA = (kX3 ? 2 : 1) * kTileBytesA;
   static constexpr int kStageBytesB = (kX3 ? 2 : kBParts) * kTileBytesB;
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__((PCfg<TBK, TBN, MODE>::kThreads), 1) conv_gemm
           tcgen05_fence_after();
           if constexpr (B16) {
             // A: 8-row groups of [hi 8 x TBK bf16 | lo 8 x TBK bf16] where the fp32 rows were; B: dense bf16 planes
-            const uint64_t a_hi = make_kmajor_desc16<TBK>(sA + s * kStageBytesA, 8 * TBK * 4);
+            const uint64_t a_hi = make_kmajor_desc16<TBK>(sA + s * kStageBytesA, C_::kDirect ? 8 * TBK * 2 : 8 * TBK * 4);
             const uint64_t a_lo = make_kmajor_desc16<TBK>(sA + s * kStageBytesA + 8 * TBK * 2, 8 * TBK * 4);
             const uint64_t b_hi = make_kmajor_desc16<TBK>(sB + s * kStageBytesB, 8 * TBK * 2);
             const uint64_t b_lo = make_kmajor_desc16<TBK>(sB + s * kStageBytesB + kTileBytesB, 8 * TBK * 2);
@@ -920,19 +923,20 @@ int launch_tc_persist(const bd_gemm_desc& d, const TileGeom& g, int items, cudaS
   using C_ = PCfg<TBK, TBN, MODE>;
   alignas(64) CUtensorMap map_a, map_b, map_b_lo;
   const long long s0 = d.xs_0, s1 = d.J1 > 1 ? d.xs_1 : s0 * d.J0, sb = items > 1 ? d.xs_b : s1 * d.J1;
+  constexpr int ES = C_::kDirect ? 2 : 4;            // bytes per element of the A tensor
   cuuint64_t adim[5] = {(cuuint64_t)d.Cin, (cuuint64_t)d.J0, (cuuint64_t)d.J1, (cuuint64_t)items, 1};
-  cuuint64_t astr[4] = {(cuuint64_t)s0 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)sb * 4, 0};
+  cuuint64_t astr[4] = {(cuuint64_t)s0 * ES, (cuuint64_t)s1 * ES, (cuuint64_t)sb * ES, 0};
   cuuint32_t abox[5] = {(cuuint32_t)TBK, (cuuint32_t)g.R0, (cuuint32_t)g.R1, 1, 1};
   int arank = 4;
   if (g.stride4) {
     arank = 5;
     adim[1] = 4; adim[2] = (cuuint64_t)d.J0 / 4; adim[3] = (cuuint64_t)d.J1; adim[4] = (cuuint64_t)items;
-    astr[0] = (cuuint64_t)s0 * 4; astr[1] = (cuuint64_t)s0 * 16; astr[2] = (cuuint64_t)s1 * 4; astr[3] = (cuuint64_t)sb * 4;
+    astr[0] = (cuuint64_t)s0 * ES; astr[1] = (cuuint64_t)s0 * 4 * ES; astr[2] = (cuuint64_t)s1 * ES; astr[3] = (cuuint64_t)sb * ES;
     abox[1] = 1; abox[2] = (cuuint32_t)g.R0; abox[3] = (cuuint32_t)g.R1; abox[4] = 1;
   }
   cuuint64_t bdim[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
   cuuint32_t bbox[2] = {(cuuint32_t)TBK, (cuuint32_t)TBN};
-  bool ok = encode(&map_a, d.x, arank, adim, astr, abox, TBK * 4);
+  bool ok = encode(&map_a, d.x, arank, adim, astr, abox, TBK * ES, C_::kDirect);
   if constexpr (C_::kB16) {
     cuuint64_t bstr[1] = {(cuuint64_t)d.K * 2};
     ok = ok && encode(&map_b, d.w16_hi, 2, bdim, bstr, bbox, TBK * 2, true);

@@ -71,8 +71,8 @@ __global__ void gn_gelu_apply_kernel(float* __restrict__ h, const float* __restr
 }
 
 // One warp per row.  C <= 1024, C % 4 == 0.
-template <int MAXV>
-__global__ void layer_norm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
+template <int MAXV, bool Y16>
+__global__ void layer_norm_kernel(const float* __restrict__ x, void* __restrict__ yv, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, const float* __restrict__ pos, int pos_period,
                                   long long M, int C) {
   const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -101,7 +101,8 @@ __global__ void layer_norm_kernel(const float* __restrict__ x, float* __restrict
     }
   }
   const float rstd = rsqrtf(bd_warp_sum(q) / C + 1e-5f);
-  float4* yr = reinterpret_cast<float4*>(y + m * C);
+  float4* yr = reinterpret_cast<float4*>(reinterpret_cast<float*>(yv) + (Y16 ? 0 : m * C));
+  uint2* yh = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(yv) + (Y16 ? m * C : 0));
   const float4* pr = pos ? reinterpret_cast<const float4*>(pos + (m % pos_period) * C) : nullptr;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -118,7 +119,14 @@ __global__ void layer_norm_kernel(const float* __restrict__ x, float* __restrict
         float4 p = __ldg(pr + idx);
         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
       }
-      yr[idx] = o;
+      if (Y16) {
+        uint32_t lo, hi;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(o.y), "f"(o.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(o.w), "f"(o.z));
+        yh[idx] = make_uint2(lo, hi);
+      } else {
+        yr[idx] = o;
+      }
     }
   }
 }
@@ -190,16 +198,20 @@ int bd_gn_gelu_apply(float* h, const float* mean_rstd, const float* gamma, const
   return bd_check_launch("gn_gelu_apply_kernel");
 }
 
-int bd_layer_norm(const float* x, float* y, const float* gamma, const float* beta, const float* pos, int pos_period,
-                  long long M, int C, void* stream) {
+int bd_layer_norm(const float* x, void* y, const float* gamma, const float* beta, const float* pos, int pos_period,
+                  long long M, int C, int y_bf16, void* stream) {
   BD_REQUIRE(C % 4 == 0 && C <= 1024 && M > 0, "bd_layer_norm: C must be a multiple of 4 and <= 1024 (got %d)", C);
   BD_REQUIRE(!pos || pos_period > 0, "bd_layer_norm: pos without period");
   const int warps = 8;
   dim3 grid(bd_cdiv(M, warps));
-  if (C <= 512)
-    layer_norm_kernel<4><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, pos, pos_period, M, C);
-  else
-    layer_norm_kernel<8><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, pos, pos_period, M, C);
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (y_bf16) {
+    if (C <= 512) layer_norm_kernel<4, true><<<grid, warps * 32, 0, st>>>(x, y, gamma, beta, pos, pos_period, M, C);
+    else layer_norm_kernel<8, true><<<grid, warps * 32, 0, st>>>(x, y, gamma, beta, pos, pos_period, M, C);
+  } else {
+    if (C <= 512) layer_norm_kernel<4, false><<<grid, warps * 32, 0, st>>>(x, y, gamma, beta, pos, pos_period, M, C);
+    else layer_norm_kernel<8, false><<<grid, warps * 32, 0, st>>>(x, y, gamma, beta, pos, pos_period, M, C);
+  }
   return bd_check_launch("layer_norm_kernel");
 }
 

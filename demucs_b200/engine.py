@@ -255,7 +255,8 @@ class Engine:
               xs=(0, 0, None, 1), os_=(0, 0, None), bias=None, a_mode=_lib.A_NONE, a_stats=None,
               a_stats_stride=0, a_gamma=None, a_beta=None, act=_lib.ACT_NONE, rowbias=None, rowbias_period=0,
               resid=None, scale=None, addend=None, convt=0, O0=0, stats_out=None, stat=(0, 0, 0),
-              e_stats=None, e_gamma=None, e_beta=None, oc_split=0, oc_stride=0, tc=True) -> None:
+              e_stats=None, e_gamma=None, e_beta=None, oc_split=0, oc_stride=0, tc=True, xf=False, x16=False,
+              out16=False) -> None:
         d = GemmDesc()
         I0 = M if I0 is None else I0
         d.M, d.N, d.K, d.Cin, d.taps = M, N, len(taps) * Cin, Cin, len(taps)
@@ -275,13 +276,17 @@ class Engine:
         d.oc_split, d.oc_stride = oc_split, oc_stride
         d.stats_out = ptr(stats_out)
         d.stat_div, d.stat_mul, d.stat_mod = stat
-        d.math = _lib.MATH_FP32 if not tc else _GEMM_MATH[self.mode]
+        # "bf16" mode: bf16 operands inside the transformer (two thirds of the flops, all of it in LayerScale'd residual
+        # branches), single-pass tf32 for the convolutions of the U-Net, whose activations are the main signal path
+        d.math = _lib.MATH_FP32 if not tc else (_lib.MATH_TF32 if (self.mode == "bf16" and not xf) else _GEMM_MATH[self.mode])
         if d.math in (_lib.MATH_BF16X3, _lib.MATH_BF16) and Cin % 16 == 0 and _lib.TEST_HOOK is None:
             hi, lo = self._w16(w)
             d.w16_hi, d.w16_lo = ptr(hi), ptr(lo)
+        d.x_bf16, d.out_bf16 = int(x16), int(out16)
         K = len(taps) * Cin
         rows_in = (M // (I1 * I0)) * d.J1 * d.J0          # input positions (each read once, algorithmically)
-        nbytes = 4.0 * (rows_in * Cin + N * K + (M * (N if convt else n_out) if out is not None else 0))
+        nbytes = (2.0 if x16 else 4.0) * rows_in * Cin + (2.0 if d.w16_hi else 4.0) * N * K + \
+            (2.0 if out16 else 4.0) * (M * (N if convt else n_out) if out is not None else 0)
         nbytes += 4.0 * M * n_out * ((resid is not None) + (addend is not None))
         arm = "simt"
         tile = 128 if N > 64 else 64 if N > 32 else 32 if (N > 16 or act == _lib.ACT_GLU) else 16
@@ -360,6 +365,8 @@ class Engine:
         """x += gamma_1 * MHA(q=x_normed, k=v=kv_normed); both inputs are already layer-normed."""
         W, D, H = self.W, self.cfg.transformer_dim, self.cfg.t_heads
         Win, bin_ = W[f"{p}.{attn}.in_proj_weight"], W[f"{p}.{attn}.in_proj_bias"]
+        if self.mode == "bf16":
+            return self._attention_block_bf16(key, x, kv_src, Win, bin_, B, Tq, Tk, tag)
         att = self._buf(key, f"att{tag}", B * Tq * D)
         nws = _lib.call_value("bd_attention_workspace", B, H, Tq, Tk, self._math())
         ws = self._buf(key, f"att_ws{tag}", nws) if nws else None
@@ -368,18 +375,41 @@ class Engine:
         nk = {_lib.MATH_FP32: 1, _lib.MATH_TF32: 2, _lib.MATH_TF32X3: 4, _lib.MATH_BF16X3: 4, _lib.MATH_BF16: 4}[self._math()]
         if kv_src is None:  # self attention: one packed projection
             qkv = self._buf(key, f"qkv{tag}", B * Tq * 3 * D)
-            self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv)
+            self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv, xf=True)
             self._k("bd_attention", ptr(qkv), qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, ptr(att),
                     B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._math(), ptr(ws), self._stream(),
                     flops=4.0 * B * Tq * Tq * D, nbytes=4.0 * B * Tq * D * 4, label=label, kernels=nk)
         else:
             q = self._buf(key, f"q{tag}", B * Tq * D)
             kv = self._buf(key, f"kv{tag}", B * Tk * 2 * D)
-            self._gemm(M=B * Tq, N=D, Cin=D, x=x, w=Win[:D], bias=bin_[:D], out=q)
-            self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv)
+            self._gemm(M=B * Tq, N=D, Cin=D, x=x, w=Win[:D], bias=bin_[:D], out=q, xf=True)
+            self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv, xf=True)
             self._k("bd_attention", ptr(q), ptr(kv), kv.data_ptr() + 4 * D, ptr(att),
                     B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._math(), ptr(ws), self._stream(),
                     flops=4.0 * B * Tq * Tk * D, nbytes=4.0 * B * (2 * Tq + 2 * Tk) * D, label=label, kernels=nk)
+        return att
+
+    def _attention_block_bf16(self, key, x, kv_src, Win, bin_, B: int, Tq: int, Tk: int, tag: str):
+        """The "bf16" mode's form of the block: the layer-normed inputs, the projections and the attention output
+        are bf16 tensors that only ever travel from one tensor-core kernel to the next (TMA reads them in operand form,
+        no conversion passes); the residual stream they are added to stays fp32."""
+        D, H = self.cfg.transformer_dim, self.cfg.t_heads
+        bf = torch.bfloat16
+        att = self._buf(key, f"att16{tag}", B * Tq * D, bf)
+        if kv_src is None:
+            qkv = self._buf(key, f"qkv16{tag}", B * Tq * 3 * D, bf)
+            self._gemm(M=B * Tq, N=3 * D, Cin=D, x=x, w=Win, bias=bin_, out=qkv, xf=True, x16=True, out16=True)
+            self._k("bd_attention_bf16", ptr(qkv), qkv.data_ptr() + 2 * D, qkv.data_ptr() + 4 * D, ptr(att),
+                    B, H, Tq, Tq, 3 * D, 3 * D, 3 * D, D, self._stream(),
+                    flops=4.0 * B * Tq * Tq * D, nbytes=2.0 * B * Tq * D * 4, label="attention_tc")
+        else:
+            q = self._buf(key, f"q16{tag}", B * Tq * D, bf)
+            kv = self._buf(key, f"kv16{tag}", B * Tk * 2 * D, bf)
+            self._gemm(M=B * Tq, N=D, Cin=D, x=x, w=Win[:D], bias=bin_[:D], out=q, xf=True, x16=True, out16=True)
+            self._gemm(M=B * Tk, N=2 * D, Cin=D, x=kv_src, w=Win[D:], bias=bin_[D:], out=kv, xf=True, x16=True, out16=True)
+            self._k("bd_attention_bf16", ptr(q), ptr(kv), kv.data_ptr() + 2 * D, ptr(att),
+                    B, H, Tq, Tk, D, 2 * D, 2 * D, D, self._stream(),
+                    flops=4.0 * B * Tq * Tk * D, nbytes=2.0 * B * (2 * Tq + 2 * Tk) * D, label="attention_tc")
         return att
 
     def _math(self) -> int:
@@ -389,30 +419,33 @@ class Engine:
 
     def _ln(self, x, y, p: str, M: int, pos=None, period=0):
         D = self.cfg.transformer_dim
+        y16 = y.dtype == torch.bfloat16
         self._k("bd_layer_norm", ptr(x), ptr(y), ptr(self.W[f"{p}.weight"]), ptr(self.W[f"{p}.bias"]),
-                ptr(pos), period, M, D, self._stream(), nbytes=8.0 * M * D)
+                ptr(pos), period, M, D, int(y16), self._stream(), nbytes=(6.0 if y16 else 8.0) * M * D)
 
     def _transformer_layer(self, key, x, other_normed, p: str, cross: bool, B: int, T: int, Tk: int, tag: str):
         """One MyTransformerEncoderLayer / CrossTransformerEncoderLayer, norm_first, in place on x
         (transformer.py:363-372, 495-500)."""
         W, D, Hd = self.W, self.cfg.transformer_dim, self.cfg.ffn_dim
         M = B * T
-        ln = self._buf(key, f"ln{tag}", M * D)
+        b16 = self.mode == "bf16"      # GEMM-to-GEMM tensors (layer-norm outputs, FFN hidden) are stored as bf16
+        adt = torch.bfloat16 if b16 else torch.float32
+        ln = self._buf(key, f"ln{tag}", M * D, adt)
         self._ln(x, ln, f"{p}.norm1", M)
         att = self._attention_block(key, ln, other_normed if cross else None, p,
                                     "cross_attn" if cross else "self_attn", B, T, Tk, tag)
         a = "cross_attn" if cross else "self_attn"
         self._gemm(M=M, N=D, Cin=D, x=att, w=W[f"{p}.{a}.out_proj.weight"], bias=W[f"{p}.{a}.out_proj.bias"],
-                   out=x, resid=x, scale=W[f"{p}.gamma_1.scale"])
+                   out=x, resid=x, scale=W[f"{p}.gamma_1.scale"], xf=True, x16=b16)
         self._ln(x, ln, f"{p}.norm3" if cross else f"{p}.norm2", M)
-        hbuf = self._buf(key, f"ffn{tag}", M * Hd)
+        hbuf = self._buf(key, f"ffn{tag}", M * Hd, adt)
         self._gemm(M=M, N=Hd, Cin=D, x=ln, w=W[f"{p}.linear1.weight"], bias=W[f"{p}.linear1.bias"], out=hbuf,
-                   act=_lib.ACT_GELU)
+                   act=_lib.ACT_GELU, xf=True, x16=b16, out16=b16)
         sums = self._buf(key, f"no_sums{tag}", 2 * B, torch.float64, zero=True)   # finalize clears it again
         mr = self._buf(key, f"no_mr{tag}", 2 * B)
         self._gemm(M=M, N=D, Cin=Hd, x=hbuf, w=W[f"{p}.linear2.weight"], bias=W[f"{p}.linear2.bias"], out=x,
                    resid=x, scale=W[f"{p}.gamma_2.scale"], I1=1, I0=T, J0=T, xs=(T * Hd, 0, Hd, 1),
-                   os_=(T * D, 0, D), stats_out=sums, stat=(T, 1, 1))
+                   os_=(T * D, 0, D), stats_out=sums, stat=(T, 1, 1), xf=True, x16=b16)
         self._k("bd_finalize_group_stats", ptr(sums), ptr(mr), B, float(T * D), self._stream())
         self._k("bd_group_norm_apply", ptr(x), ptr(mr), ptr(W[f"{p}.norm_out.weight"]),
                 ptr(W[f"{p}.norm_out.bias"]), B, T, D, self._stream(), nbytes=8.0 * B * T * D)
@@ -567,8 +600,9 @@ class Engine:
                     self._transformer_layer(key, xt_, None, f"{ct}.layers_t.{i}", False, B, T2, T2, "_t")
                 else:
                     # both sides attend to the other's *pre-update* tokens (transformer.py:669-672)
-                    kf = self._buf(key, "kn_f", Mt * D)   # keys for the freq side = LN2(xt)
-                    kt = self._buf(key, "kn_t", Mf * D)   # keys for the time side = LN2_t(old x)
+                    kdt = torch.bfloat16 if self.mode == "bf16" else torch.float32
+                    kf = self._buf(key, "kn_f", Mt * D, kdt)   # keys for the freq side = LN2(xt)
+                    kt = self._buf(key, "kn_t", Mf * D, kdt)   # keys for the time side = LN2_t(old x)
                     self._ln(xt_, kf, f"{ct}.layers.{i}.norm2", Mt)
                     self._ln(x, kt, f"{ct}.layers_t.{i}.norm2", Mf)
                     self._transformer_layer(key, x, kf, f"{ct}.layers.{i}", True, B, T * Fb, T2, "_f")

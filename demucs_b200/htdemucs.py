@@ -40,11 +40,13 @@ class HTDemucs(nn.Module):
 
     Args mirror reference ``HTDemucs.__init__`` (htdemucs.py:56-135); options outside the
     released Demucs-v4 space raise ``UnsupportedConfig``.  Extra keyword-only arguments:
-      mode: "fp32" (bit-faithful FFMA contractions) or "tf32" (tcgen05 tensor cores).
+      mode: "strict" (default: tcgen05 tensor cores with error-compensated bf16 hi/lo operands, per-stem rel-L2 <= 1e-4
+            against the fp32 reference), "bf16" (bf16 tensors and MMAs through the transformer, <= 1e-2), "fp32"
+            (CUDA-core FFMA contractions), "tf32x3" / "tf32" (the kind::tf32 forms).
       init_seed / layer_scale: synthetic initialisation (``weights.init_weights``).
     """
 
-    def __init__(self, sources, *, mode: str = "fp32", init_seed: int = 0,
+    def __init__(self, sources, *, mode: str = "strict", init_seed: int = 0,
                  layer_scale: tp.Optional[float] = None, **kwargs):
         super().__init__()
         self.cfg = HTDemucsConfig.from_reference_kwargs(sources=list(sources), **kwargs)
@@ -69,7 +71,7 @@ class HTDemucs(nn.Module):
 
     # ---- construction helpers ------------------------------------------------------------
     @classmethod
-    def from_reference(cls, module, mode: str = "fp32") -> "HTDemucs":
+    def from_reference(cls, module, mode: str = "strict") -> "HTDemucs":
         """Build from a live reference ``demucs.htdemucs.HTDemucs`` (SURVEY.md 8b weight hand-off)."""
         args, kwargs = module._init_args_kwargs
         kwargs = dict(kwargs)
@@ -81,7 +83,7 @@ class HTDemucs(nn.Module):
         return model
 
     @classmethod
-    def from_config(cls, cfg: HTDemucsConfig, state=None, mode: str = "fp32", init_seed: int = 0,
+    def from_config(cls, cfg: HTDemucsConfig, state=None, mode: str = "strict", init_seed: int = 0,
                     layer_scale: tp.Optional[float] = None) -> "HTDemucs":
         kw = cfg.reference_kwargs()
         sources = kw.pop("sources")

@@ -91,6 +91,10 @@ typedef struct bd_gemm_desc {
   int math;            /* BD_MATH_* */
   const void* w16_hi;  /* BD_MATH_BF16X3 / BD_MATH_BF16: bf16 [N, K] = bf16_rn(w) */
   const void* w16_lo;  /* BD_MATH_BF16X3: bf16 [N, K] = bf16_rn(w - w16_hi) */
+  /* bf16 storage (the "bf16" mode's transformer: tensors that only ever travel from one GEMM / attention to the next):
+   * x_bf16: x is bf16 (element strides as above; BD_MATH_BF16 only, Cin % 64 == 0, read by TMA, no conversion);
+   * out_bf16: out is bf16 (same index arithmetic in elements).  resid / addend / rowbias / statistics stay fp32. */
+  int x_bf16, out_bf16;
 } bd_gemm_desc;
 
 const char* bd_last_error(void);
@@ -168,9 +172,10 @@ int bd_dconv_expand_update(const float* h, int ldh, int hid, const float* mean_r
 int bd_gn_gelu_apply(float* h, const float* mean_rstd, const float* gamma, const float* beta, long long M, int C,
                      long long rows_per_item, int slabs_per_item, void* stream);
 /* nn.LayerNorm(C) (transformer.py:434-436,591-592,597-598) with optional additive table
- * pos[(m % pos_period)*C + c] (positional embedding, transformer.py:655-663). y may alias x. */
-int bd_layer_norm(const float* x, float* y, const float* gamma, const float* beta, const float* pos,
-                  int pos_period, long long M, int C, void* stream);
+ * pos[(m % pos_period)*C + c] (positional embedding, transformer.py:655-663). y may alias x; y_bf16 != 0: y is a
+ * bf16 tensor (it feeds tensor-core GEMMs only). */
+int bd_layer_norm(const float* x, void* y, const float* gamma, const float* beta, const float* pos,
+                  int pos_period, long long M, int C, int y_bf16, void* stream);
 /* (sum, sumsq) per item of x [B, n] (for norm_out, transformer.py:372,500). */
 int bd_item_stats(const float* x, double* sums, int B, long long n, void* stream);
 /* MyGroupNorm(1) apply: x[b, t, c] = (x - mean_b) * rstd_b * gamma[c] + beta[c], in place. */
@@ -184,6 +189,11 @@ int bd_group_norm_apply(float* x, const float* mean_rstd, const float* gamma, co
 long long bd_attention_workspace(int B, int H, int Tq, int Tk, int math);
 int bd_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk,
                  int ldq, int ldk, int ldv, int ldo, int math, float* ws, void* stream);
+
+/* K6 on bf16 tensors (the "bf16" mode): q [B,Tq,ldq] / k,v [B,Tk,ld*] / o [B,Tq,ldo] are bf16, read by TMA with no
+ * conversion pass and no workspace; fp32 softmax statistics and accumulation. */
+int bd_attention_bf16(const void* q, const void* k, const void* v, void* o, int B, int H, int Tq, int Tk,
+                      int ldq, int ldk, int ldv, int ldo, void* stream);
 
 /* K8 (apply.py:257-301 + utils.py:38-54): overlap-add of separated segments.
  * The window of `length` samples is tiled by nseg segments starting at i*stride; the caller holds the

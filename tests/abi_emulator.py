@@ -271,7 +271,8 @@ def bd_gn_gelu_apply(h, mr, gamma, beta, M, Cc, rows_per_item, spi, stream):
     hv[:] = gelu((hv - st[:, :1]) * st[:, 1:2] * f32(gamma, Cc) + f32(beta, Cc))
 
 
-def bd_layer_norm(x, y, gamma, beta, pos, period, M, Cc, stream):
+def bd_layer_norm(x, y, gamma, beta, pos, period, M, Cc, y_bf16, stream):
+    assert not y_bf16, "the emulator keeps fp32 tensors"
     xv = f32(x, M * Cc).reshape(M, Cc).astype(np.float64)
     mean = xv.mean(1, keepdims=True)
     var = xv.var(1, keepdims=True)

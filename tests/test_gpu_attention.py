@@ -49,3 +49,30 @@ def test_attention(B, H, Tq, Tk, math_mode, tol):
     e = rel_l2(out.cpu(), want.cpu())
     print(f"attention math={math_mode} B{B} H{H} {Tq}x{Tk}: rel-L2 {e:.2e}")
     assert e < tol
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk", [(2, 8, 2688, 2688), (1, 8, 1344, 2688), (2, 2, 352, 173), (1, 1, 129, 1)])
+def test_attention_bf16_tensors(B, H, Tq, Tk):
+    """bf16 q / k / v read by TMA without a conversion pass, bf16 output: against fp64 on the same bf16 inputs."""
+    g = torch.Generator().manual_seed(4)
+    D = 64 * H
+    if Tq == Tk:
+        qkv = torch.randn(B, Tq, 3 * D, generator=g).to(DEV).to(torch.bfloat16)
+        q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+        ptrs, lds = (qkv.data_ptr(), qkv.data_ptr() + 2 * D, qkv.data_ptr() + 4 * D), (3 * D,) * 3
+    else:
+        qb = torch.randn(B, Tq, D, generator=g).to(DEV).to(torch.bfloat16)
+        kv = torch.randn(B, Tk, 2 * D, generator=g).to(DEV).to(torch.bfloat16)
+        q, k, v = qb, kv[..., :D], kv[..., D:]
+        ptrs, lds = (qb.data_ptr(), kv.data_ptr(), kv.data_ptr() + 2 * D), (D, 2 * D, 2 * D)
+    out = torch.full((B, Tq, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    _lib.call("bd_attention_bf16", ptrs[0], ptrs[1], ptrs[2], out.data_ptr(), B, H, Tq, Tk, lds[0], lds[1], lds[2], D, 0)
+    torch.cuda.synchronize()
+    qh = q.double().view(B, Tq, H, 64).transpose(1, 2)
+    kh = k.double().view(B, Tk, H, 64).transpose(1, 2)
+    vh = v.double().view(B, Tk, H, 64).transpose(1, 2)
+    want = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Tq, D)
+    assert not torch.isnan(out.float()).any()
+    e = rel_l2(out.float().cpu(), want.cpu())
+    print(f"bf16-tensor attention B{B} H{H} {Tq}x{Tk}: rel-L2 {e:.2e}")
+    assert e < 6e-3

@@ -165,3 +165,53 @@ def test_encoder_conv0_mma(channel_major, math_mode, tol):
     want = F.gelu(F.conv1d(xn, w.double(), b.double(), stride=4))[..., :Io]  # [B*I1, cout, Io]
     want = want.reshape(B, I1, cout, Io).permute(0, 1, 3, 2)
     assert rel_l2(out.cpu(), want.float()) < tol
+
+
+@pytest.mark.parametrize("M,N,K,act", [(2688, 1536, 512, _lib.ACT_NONE), (4000, 2048, 512, _lib.ACT_GELU),
+                                       (1344 * 2, 512, 2048, _lib.ACT_NONE), (300, 64, 64, _lib.ACT_NONE)])
+@pytest.mark.parametrize("out16", [0, 1])
+def test_gemm_bf16_tensors(M, N, K, act, out16):
+    """bf16 A tensor read by TMA in operand form (BD_MATH_BF16 + x_bf16), fp32 or bf16 output, fp32 residual: against an
+    fp64 product of the SAME bf16-rounded operands (so only accumulation order and the output rounding differ)."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    w_hi = w.to(torch.bfloat16)
+    b = torch.randn(N, generator=g).to(DEV)
+    r = torch.randn(M, N, generator=g).to(DEV) if not out16 else None
+    sc = torch.randn(N, generator=g).to(DEV) if not out16 else None
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16 if out16 else torch.float32)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.Cin, d.taps = M, N, K, K, 1
+    d.I1, d.I0, d.m1, d.m0, d.J1, d.J0 = 1, M, 1, 1, 1, M
+    d.xs_b, d.xs_1, d.xs_0, d.xs_c = M * K, 0, K, 1
+    d.os_b, d.os_1, d.os_0 = M * N, 0, N
+    d.x, d.w, d.bias, d.out = ptr(x), ptr(w), ptr(b), ptr(out)
+    d.act, d.resid, d.scale = act, ptr(r), ptr(sc)
+    d.stat_div, d.stat_mul, d.stat_mod = M, 1, 1
+    d.math, d.w16_hi, d.x_bf16, d.out_bf16 = _lib.MATH_BF16, ptr(w_hi), 1, out16
+    assert _lib.lib().bd_conv_gemm_arm(C.byref(d)) // 1000 == 64
+    _lib.call("bd_conv_gemm", C.byref(d), 0)
+    torch.cuda.synchronize()
+    want = x.double() @ w_hi.double().t() + b.double()
+    if act == _lib.ACT_GELU:
+        want = F.gelu(want)
+    if r is not None:
+        want = r.double() + sc.double() * want
+    e = rel_l2(out.float().cpu(), want.cpu())
+    print(f"bf16-tensor gemm {M}x{N}x{K} out16={out16}: rel-L2 {e:.2e}")
+    assert e < (3e-3 if out16 else 2e-6)
+
+
+def test_layer_norm_bf16_output():
+    g = torch.Generator().manual_seed(2)
+    M, Cc = 3001, 512
+    x = torch.randn(M, Cc, generator=g).to(DEV)
+    gam, bet = torch.randn(Cc, generator=g).to(DEV), torch.randn(Cc, generator=g).to(DEV)
+    pos = torch.randn(7, Cc, generator=g).to(DEV)
+    y = torch.empty(M, Cc, device=DEV, dtype=torch.bfloat16)
+    _lib.call("bd_layer_norm", ptr(x), ptr(y), ptr(gam), ptr(bet), ptr(pos), 7, M, Cc, 1, 0)
+    torch.cuda.synchronize()
+    want = F.layer_norm(x.double(), (Cc,), gam.double(), bet.double(), 1e-5) + pos.double()[torch.arange(M, device=DEV) % 7]
+    assert rel_l2(y.float().cpu(), want.cpu()) < 3e-3
+    assert (y.float() - want.float().to(torch.bfloat16).float()).abs().max() <= 1.6e-2 * want.abs().max()

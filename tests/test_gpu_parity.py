@@ -198,7 +198,9 @@ def test_apply_model_full_size_round_trip_properties():
     short = mix[..., :cfg.segment_length].contiguous()
     a = D.apply_model(model, short, shifts=0, split=False, device=DEV)
     b = model(short.to(DEV)).cpu()
-    assert rel_l2(a, b) < 1e-6
+    # two forwards of the same input: the GroupNorm partial sums meet through order-dependent atomics (last-bit noise),
+    # which this random-weight network amplifies ~40x (tools/dev_determinism.py: 1.4e-5 run to run in this mode)
+    assert rel_l2(a, b) < 5e-5
 
 
 def test_separator_front_door():
@@ -229,18 +231,21 @@ def test_errors_are_loud():
         D.HTDemucs.from_config(cfg, init_seed=0).forward(torch.zeros(1, 2, 4096))   # CPU tensors: no fallback
 
 
-FAST_TOL = 1e-2   # single-pass TF32 tensor-core mode: the north_star's reduced-precision (bf16-class) bound
+BF16_TOL = 1e-2   # the north_star's bound for the bf16 mode (per-stem relative L2)
+TF32_TOL = 6e-3   # "tf32" (single-pass kind::tf32) is an auxiliary mode with NO north_star tolerance class: it misses the
+#                   1e-4 bound by construction (10-bit operands); this is its own measured envelope, kept as a regression guard
 
 
+@pytest.mark.parametrize("mode,tol", [("bf16", BF16_TOL), ("tf32", TF32_TOL)])
 @pytest.mark.parametrize("name", ["htdemucs_default.npz", "htdemucs_ls05.npz"])
-def test_forward_htdemucs_tf32_mode(name):
-    """Single-pass TF32 on the tcgen05 arm (10-bit mantissas, truncated): measured ~1e-3 per stem, i.e.
-    inside the reduced-precision bound (<= 1e-2) but NOT the fp32-class bound (<= 1e-4), which the
-    "fp32" mode (and the error-compensated "tf32x3" mode) meet."""
+def test_forward_htdemucs_reduced_precision_modes(name, mode, tol):
+    """"bf16": bf16 tensors and kind::f16 MMAs through the transformer, single-pass tf32 convolutions -- the
+    north_star's bf16 tolerance, per-stem relative L2 <= 1e-2, on both weight fixtures, every block tap included.
+    "tf32": single-pass kind::tf32 everywhere (auxiliary; its own envelope)."""
     g = golden(name)
     cfg = htdemucs_config()
     W, mix = forward_fixture_inputs(g, cfg)
-    eng = Engine(cfg, W, DEV, mode="tf32")
+    eng = Engine(cfg, W, DEV, mode=mode)
     taps = {}
     got = eng.forward(mix.to(DEV), taps)
     torch.cuda.synchronize()
@@ -249,16 +254,17 @@ def test_forward_htdemucs_tf32_mode(name):
         if key.startswith("tap."):
             errs[key[4:]] = rel_l2(strided(taps[key[4:]].contiguous(), int(g["tap_stride"])), g[key])
     e_out = rel_l2(strided(got, int(g["stride"])), g["out"])
-    print(name, "tf32 out rel-L2", e_out, "worst tap", max(errs.items(), key=lambda kv: kv[1]))
-    assert max(errs.values()) < FAST_TOL
+    print(name, mode, "out rel-L2", e_out, "worst tap", max(errs.items(), key=lambda kv: kv[1]))
+    assert max(errs.values()) < tol
     with torch.no_grad():
         want = htdemucs_forward(W, cfg, mix)
     stems = stem_errors(got.cpu(), want)
     print("per-stem", stems)
-    assert max(stems) < FAST_TOL
+    assert max(stems) < tol
 
 
-def test_forward_blocks_small_tf32_mode():
+@pytest.mark.parametrize("mode,tol", [("bf16", BF16_TOL), ("tf32", TF32_TOL), ("strict", 1e-4)])
+def test_forward_blocks_small_tc_modes(mode, tol):
     """Small geometry through the tensor-core arm (16/32-float k-blocks, R0 < 128 tiles, 3-tap transposed
     convs, narrow tiles): every block within TF32 rounding of the fp32 oracle."""
     g = golden("small_ls05.npz")
@@ -267,13 +273,13 @@ def test_forward_blocks_small_tf32_mode():
     taps_o, taps = {}, {}
     with torch.no_grad():
         want = htdemucs_forward(W, cfg, mix, taps_o)
-    eng = Engine(cfg, W, DEV, mode="tf32")
+    eng = Engine(cfg, W, DEV, mode=mode)
     got = eng.forward(mix.to(DEV), taps)
     torch.cuda.synchronize()
     errs = {k: rel_l2(taps[k].cpu(), v) for k, v in taps_o.items()}
-    print("small tf32 taps", {k: f"{e:.1e}" for k, e in errs.items()})
-    assert max(errs.values()) < FAST_TOL
-    assert max(stem_errors(got.cpu(), want)) < FAST_TOL
+    print("small", mode, "taps", {k: f"{e:.1e}" for k, e in errs.items()})
+    assert max(errs.values()) < tol
+    assert max(stem_errors(got.cpu(), want)) < tol
 
 
 @pytest.mark.parametrize("mode", ["strict", "tf32x3"])
@@ -303,12 +309,13 @@ def test_forward_htdemucs_strict_modes(name, mode):
     assert max(stems) < STEM_TOL
 
 
-def test_htdemucs_6s_shifts2_tf32x3():
+@pytest.mark.parametrize("mode,tol", [("strict", STEM_TOL), ("bf16", BF16_TOL)])
+def test_htdemucs_6s_shifts2(mode, tol):
     """BASELINE config 3 in miniature: the 6-stem geometry (htdemucs_6s), overlap 0.25, shifts=2, two segments,
-    in the fp32-accurate tensor-core mode, against the oracle drawing the same shift offsets."""
+    in the default (fp32-accurate) and the bf16 mode, against the oracle drawing the same shift offsets."""
     from demucs_b200.config import htdemucs_6s_config
     cfg = htdemucs_6s_config()
-    model = D.HTDemucs.from_config(cfg, init_seed=3, mode="tf32x3").to(DEV)
+    model = D.HTDemucs.from_config(cfg, init_seed=3, mode=mode).to(DEV)
     mix = synth_mix(1, 400000, 77)
     random.seed(11)
     out = D.apply_model(model, mix, shifts=2, split=True, overlap=0.25, device=DEV)
@@ -318,16 +325,18 @@ def test_htdemucs_6s_shifts2_tf32x3():
     with torch.no_grad():
         want = apply_model_oracle((W, cfg), mix, shifts=2, split=True, overlap=0.25)
     errs = stem_errors(out, want)
-    print("6s shifts=2 per-stem", errs)
-    assert max(errs) < STEM_TOL
+    print("6s shifts=2", mode, "per-stem", errs)
+    assert max(errs) < tol
 
 
-def test_bag_of_four_single_source_members_tf32():
+@pytest.mark.parametrize("mode,tol", [("bf16", BF16_TOL), ("strict", STEM_TOL)])
+def test_bag_of_four_single_source_members(mode, tol):
     """BASELINE config 4 in miniature (htdemucs_ft: four fine-tuned members, member i contributes source i only,
-    demucs/remote/htdemucs_ft.yaml) in the reduced-precision mode, against the oracle's weighted sum."""
+    demucs/remote/htdemucs_ft.yaml) in the bf16 mode the config names (and the default one), against the oracle's
+    weighted sum."""
     cfg = htdemucs_config()
     weights = [[1.0 if s == m else 0.0 for s in range(4)] for m in range(4)]
-    models = [D.HTDemucs.from_config(cfg, init_seed=10 + m, mode="tf32").to(DEV) for m in range(4)]
+    models = [D.HTDemucs.from_config(cfg, init_seed=10 + m, mode=mode).to(DEV) for m in range(4)]
     mix = synth_mix(1, 300000, 5)
     out = D.apply_model(D.BagOfModels(models, weights), mix, shifts=0, split=True, overlap=0.25, device=DEV)
     want = torch.zeros_like(out)
@@ -336,15 +345,15 @@ def test_bag_of_four_single_source_members_tf32():
             part = apply_model_oracle((init_weights(cfg, 10 + m), cfg), mix, shifts=0, split=True, overlap=0.25)
             want[:, m] = part[:, m]
     errs = stem_errors(out, want)
-    print("bag of 4 per-stem", errs)
-    assert max(errs) < FAST_TOL
+    print("bag of 4", mode, "per-stem", errs)
+    assert max(errs) < tol
 
 
 def test_full_size_batch_64_items_are_independent():
     """bench.py runs one 64-segment forward per step (11 M rows in the first layers): every item must come out as it
     does alone (guards the 32-bit row arithmetic and the per-item statistics slabs at that size)."""
     cfg = htdemucs_config()
-    eng = Engine(cfg, init_weights(cfg, 0, layer_scale=0.5), DEV, mode="tf32x3")
+    eng = Engine(cfg, init_weights(cfg, 0, layer_scale=0.5), DEV, mode="strict")
     mix = synth_mix(64, cfg.segment_length, 21).to(DEV)
     full = eng.forward(mix).clone()
     assert torch.isfinite(full).all()
@@ -353,18 +362,19 @@ def test_full_size_batch_64_items_are_independent():
         assert rel_l2(one.cpu(), full[b:b + 1].cpu()) < 2e-6, b
 
 
-def test_forward_htdemucs_short_input_batch3_tf32():
+@pytest.mark.parametrize("mode,tol", [("strict", STEM_TOL), ("bf16", BF16_TOL)])
+def test_forward_htdemucs_short_input_batch3(mode, tol):
     """The htdemucs geometry with an input shorter than the training segment (the model pads it, htdemucs.py:536-542)
     and an odd batch, on the single-pass tensor-core arm: exercises the ragged tails of the mma.sync kernels."""
     cfg = htdemucs_config()
     W = init_weights(cfg, 4, layer_scale=0.5)
     mix = synth_mix(3, 123457, 8)
-    eng = Engine(cfg, W, DEV, mode="tf32")
+    eng = Engine(cfg, W, DEV, mode=mode)
     got = eng.forward(mix.to(DEV))
     torch.cuda.synchronize()
     assert list(got.shape) == [3, 4, 2, 123457]
     with torch.no_grad():
         want = htdemucs_forward(W, cfg, mix)
     errs = stem_errors(got.cpu(), want)
-    print("short input tf32 per-stem", errs)
-    assert max(errs) < FAST_TOL
+    print("short input", mode, "per-stem", errs)
+    assert max(errs) < tol
