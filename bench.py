@@ -45,12 +45,40 @@ def synth_track(length: int, seed: int = 1234):
     return 0.1 * torch.randn(1, 2, length, generator=g)
 
 
-def workload_config(n_gpus: int, mode: str, batch: int) -> dict:
-    return {"workload": f"htdemucs 4-stem random-init, one track of {SEGMENTS}x7.8s segments (BASELINE configs[2]), "
-                        f"apply_model overlap=0.25 shifts=0, segments sharded {SEGMENTS}/N per GPU",
-            "segments": SEGMENTS, "track_seconds": SEGMENTS * STRIDE / SR,
-            "forward_batch": batch, "mode": mode, "parallelism": f"segments sharded x{n_gpus}",
-            "l2": "inputs larger than L2 (132 MB track, multi-GB activations per step)"}
+TEN_MIN = 600 * SR           # 26 460 000 samples -> 103 segments per pass
+# name -> (label, track length, shifts, default mode); the first is the headline (BASELINE configs[2])
+WORKLOADS = {
+    "configs2": (f"htdemucs 4-stem random-init, one track of {SEGMENTS}x7.8s segments (BASELINE configs[2]), "
+                 f"apply_model overlap=0.25 shifts=0, segments sharded {SEGMENTS}/N per GPU", SEGMENTS * STRIDE, 0, "strict"),
+    "6s_10min": ("htdemucs_6s 6-stem random-init, 10-minute track, apply_model overlap=0.25 shifts=2 (BASELINE configs[3]): "
+                 "2 x 103 segment forwards sharded across the GPUs", TEN_MIN, 2, "strict"),
+    "ft_10min": ("htdemucs_ft bag of 4 per-source htdemucs models (random-init), 10-minute track, overlap=0.25 shifts=0, bf16 mode "
+                 "(BASELINE configs[4]): 4 x 103 segment forwards, every member's segments sharded across the GPUs", TEN_MIN, 0, "bf16"),
+}
+
+
+def workload_config(n_gpus: int, mode: str, batch: int, name: str = "configs2") -> dict:
+    label, length, shifts, _ = WORKLOADS[name]
+    return {"workload": label, "name": name, "segments": -(-length // STRIDE) * max(shifts, 1) * (4 if name == "ft_10min" else 1),
+            "track_seconds": length / SR, "forward_batch": batch, "mode": mode, "parallelism": f"segments sharded x{n_gpus}",
+            "l2": "inputs larger than L2 (>= 132 MB track, multi-GB activations per step)"}
+
+
+def build_workload(name: str, mode: str, dev):
+    """(model for demucs_b200, [(weights, cfg)] + bag weights for the oracle)"""
+    import demucs_b200 as D
+    from demucs_b200.config import htdemucs_config, htdemucs_6s_config
+    from demucs_b200.weights import init_weights
+    if name == "6s_10min":
+        cfg = htdemucs_6s_config()
+        return D.HTDemucs.from_config(cfg, init_seed=0, mode=mode).to(dev), (init_weights(cfg, 0), cfg), None
+    if name == "ft_10min":
+        cfg = htdemucs_config()
+        ident = [[1.0 if s == m else 0.0 for s in range(4)] for m in range(4)]     # remote/htdemucs_ft.yaml
+        models = [D.HTDemucs.from_config(cfg, init_seed=10 + m, mode=mode).to(dev) for m in range(4)]
+        return D.BagOfModels(models, ident), [(init_weights(cfg, 10 + m), cfg) for m in range(4)], ident
+    cfg = htdemucs_config()
+    return D.htdemucs(mode=mode).to(dev), (init_weights(cfg, 0), cfg), None
 
 
 class ClockSampler:
@@ -215,13 +243,15 @@ def gpu_arm(args) -> None:
         # the stems leave each GPU for the host from the rank that made them: nothing is replicated over NVLink
         shard = Shard(gather="none")
 
-    model = D.htdemucs(mode=args.mode).to(dev)
-    eng = model.engine()
-    nseg = SEGMENTS                      # BASELINE configs[2]: 64 segments in all, 64/N per GPU (strong scaling)
-    length = nseg * STRIDE
+    label, length, shifts, _ = WORKLOADS[args.config]
+    model, oracle_models, bag_weights = build_workload(args.config, args.mode, dev)
+    eng = (model.models[0] if hasattr(model, "models") else model).engine()
+    engines = [m.engine() for m in model.models] if hasattr(model, "models") else [eng]
+    nseg = -(-length // STRIDE)          # configs[2]: 64 segments in all, 64/N per GPU (strong scaling)
     host_mix = synth_track(length).pin_memory()
     dev_mix = host_mix.to(dev)
-    kw = dict(shifts=0, split=True, overlap=0.25, batch_size=args.batch, shard=shard)
+    kw = dict(shifts=shifts, split=True, overlap=0.25, batch_size=args.batch, shard=shard)
+    import random
 
     def barrier():
         if world > 1:
@@ -229,6 +259,7 @@ def gpu_arm(args) -> None:
         torch.cuda.synchronize()
 
     def step_device():
+        random.seed(0)
         return D.apply_model(model, dev_mix, device=dev, **kw)
 
     # End-to-end step = the public call a user makes, on HOST buffers: apply_model uploads the (pinned) mix, separates,
@@ -237,6 +268,7 @@ def gpu_arm(args) -> None:
     last = {}
 
     def step_e2e():
+        random.seed(0)
         out = D.apply_model(model, host_mix, device=dev, **kw)
         a, b = shard.owned if shard is not None else (0, length)
         last["own"] = (a, b)
@@ -258,9 +290,9 @@ def gpu_arm(args) -> None:
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = eng.launches
+    l0 = sum(e.launches for e in engines)
     ms = timed(step_device, args.steps)
-    launches = torch.tensor([float(eng.launches - l0)], device=dev)
+    launches = torch.tensor([float(sum(e.launches for e in engines) - l0)], device=dev)
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         step_e2e()
@@ -272,11 +304,12 @@ def gpu_arm(args) -> None:
         dist.all_reduce(io)
         dist.all_reduce(launches)
     track_s = length / SR
+    units = workload_config(world, args.mode, args.batch, args.config)["segments"]     # segment forwards per step
     value, e2e = track_s / (ms / 1e3), track_s / (ms_e2e / 1e3)
 
     # weak-scaling companion (N > 1): 64 segments PER GPU, device-resident, same call
     weak = None
-    if world > 1 and not args.no_weak:
+    if world > 1 and not args.no_weak and args.config == "configs2":
         wlen = SEGMENTS * world * STRIDE
         wmix = synth_track(wlen).to(dev)
 
@@ -290,6 +323,13 @@ def gpu_arm(args) -> None:
 
     # per-kernel device time + algorithmic work of ONE more step, with events around every launch
     prof = perf.profile_step(eng, step_device)
+    # spot-check window (big configs): EVERY rank takes part in the sharded call -- it is a collective -- and rank 0,
+    # whose samples the window lies in, keeps the slice for the comparison with the oracle further down
+    window = (2 * STRIDE + 100000, 2 * STRIDE + 120000)
+    got_window = None
+    if args.config != "configs2" and not args.no_cpu:
+        random.seed(0)
+        got_window = D.apply_model(model, dev_mix, device=dev, **kw)[..., window[0]:window[1]].cpu()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -319,7 +359,20 @@ def gpu_arm(args) -> None:
                 "avg_launch_ms": top["ms"] / max(top["count"], 1),
                 "kernels": prof["table"]}
     cpu_baseline, parity = None, None
-    if world == 1 and not args.no_cpu:
+    if args.config != "configs2" and not args.no_cpu:
+        # spot check on a sub-window of rank 0's samples: the oracle evaluates only the segments that touch it
+        from oracle.apply_oracle import apply_model_oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        random.seed(0)
+        with torch.no_grad():
+            want = apply_model_oracle(oracle_models, host_mix, shifts=shifts, split=True, overlap=0.25,
+                                      bag_weights=bag_weights, window=window)[..., window[0]:window[1]]
+        got = got_window
+        err = max(float((got[0, s_] - want[0, s_]).norm() / want[0, s_].norm()) for s_ in range(got.shape[1]))
+        parity = {"against": "port (oracle, windowed)", "clip": f"output samples [{window[0]}, {window[1]}) of the track",
+                  "mode": args.mode, "per_stem_rel_l2_max": err, "tolerance": TOLERANCE[args.mode],
+                  "within_tolerance": (err <= TOLERANCE[args.mode]) if TOLERANCE[args.mode] else None}
+    if world == 1 and not args.no_cpu and args.config == "configs2":
         threads = os.cpu_count() or 1
         nsamp = CPU_SAMPLE_SEGMENTS
         times, kind, (cpu_mix, cpu_out) = cpu_apply_seconds(nsamp * STRIDE, 2, threads, want_output=True)
@@ -337,16 +390,16 @@ def gpu_arm(args) -> None:
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": DTYPE[args.mode], "data": "synthetic",
-            "config": workload_config(world, args.mode, args.batch),
+            "config": workload_config(world, args.mode, args.batch, args.config),
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(io[0]),
                     "d2h_bytes_per_step": int(io[1]),
                     "api": "demucs_b200.apply_model(model, pinned host mix) -> pinned host stems"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "weak": weak,
-            "model_roofline": {"segments_per_s": nseg / (ms / 1e3),
+            "model_roofline": {"segments_per_s": units / (ms / 1e3),
                                "tf32_roofline_segments_per_s_per_gpu": 1e3 / 0.742,
                                "bf16_roofline_segments_per_s_per_gpu": 1e3 / 0.377,
-                               "frac_of_tf32_model_roofline": (nseg / world / (ms / 1e3)) / (1e3 / 0.742)}}
+                               "frac_of_tf32_model_roofline": (units / world / (ms / 1e3)) / (1e3 / 0.742)}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -358,13 +411,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("BD_MODE", "strict"), choices=["fp32", "tf32", "tf32x3", "strict", "bf16"],
+    ap.add_argument("--config", default="configs2", choices=list(WORKLOADS),
+                    help="configs2 (default, the headline): 64 x 7.8 s segments; 6s_10min / ft_10min: BASELINE configs[3] / [4]")
+    ap.add_argument("--mode", default=os.environ.get("BD_MODE"), choices=["fp32", "tf32", "tf32x3", "strict", "bf16"],
                     help="strict (default): error-compensated tensor-core arithmetic, per-stem rel-L2 <= 1e-4; "
                          "bf16: reduced precision, <= 1e-2")
-    ap.add_argument("--batch", type=int, default=16, help="segments per forward")
+    ap.add_argument("--batch", type=int, default=32, help="segments per forward")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion run")
     args = ap.parse_args()
+    if args.mode is None:
+        args.mode = WORKLOADS[args.config][3]
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -45,12 +45,16 @@ def transition_weight(segment_length: int, power: float, dtype) -> torch.Tensor:
 
 def apply_single(W, cfg, mix: torch.Tensor, shifts: int, split: bool, overlap: float,
                  transition_power: float, segment: tp.Optional[float],
-                 consume_rng: bool = True) -> torch.Tensor:
+                 consume_rng: bool = True, window: tp.Optional[tp.Tuple[int, int]] = None) -> torch.Tensor:
     """shifts / split / leaf branches of apply.py:231-322 for one HTDemucs model.
 
     ``consume_rng``: the reference draws ``random.randrange(1)`` inside every forward
     (transformer.py:680, sin_random_shift=0) which advances Python's global RNG between the
     per-shift ``random.randint`` draws (apply.py:245); reproduced to keep shift offsets equal.
+
+    ``window`` = (lo, hi): only output samples [lo, hi) are wanted (a spot check on a long track): segments that do
+    not touch them are not evaluated (their RNG draws still happen); the result is exact inside the window and
+    meaningless outside.
     """
     assert transition_power >= 1
     B, C, L = mix.shape
@@ -66,7 +70,7 @@ def apply_single(W, cfg, mix: torch.Tensor, shifts: int, split: bool, overlap: f
         out = htdemucs_forward(W, cfg, padded_chunk(track, offset, length, valid))
         return center_trim(out, length)
 
-    def split_pass(track, offset0, length):
+    def split_pass(track, offset0, length, out_shift=0):
         """split branch (apply.py:257-301) over the window [offset0, offset0+length) of track."""
         if not split:
             return leaf(track, offset0, length)
@@ -80,9 +84,13 @@ def apply_single(W, cfg, mix: torch.Tensor, shifts: int, split: bool, overlap: f
             n = min(length - off, seg_len)
             # nested TensorChunk: offsets add and the length clips to the window, but padding
             # is cut from the underlying tensor (apply.py:87-96,108-124)
+            sumw[off: off + n] += weight[:n]
+            if window is not None and (off + n - out_shift <= window[0] or off - out_shift >= window[1]):
+                if consume_rng and cfg.t_layers > 0:
+                    random.randrange(1)
+                continue
             chunk = leaf(track, offset0 + off, n)
             out[..., off: off + n] += weight[:n] * chunk
-            sumw[off: off + n] += weight[:n]
         assert sumw.min() > 0
         return out / sumw
 
@@ -92,7 +100,7 @@ def apply_single(W, cfg, mix: torch.Tensor, shifts: int, split: bool, overlap: f
         acc = mix.new_zeros(B, S, C, L)
         for _ in range(shifts):
             offset = random.randint(0, max_shift)
-            res = split_pass(padded, offset, L + max_shift - offset)
+            res = split_pass(padded, offset, L + max_shift - offset, max_shift - offset)
             acc += res[..., max_shift - offset:]
         return acc / shifts
     return split_pass(mix, 0, L)
@@ -101,18 +109,19 @@ def apply_single(W, cfg, mix: torch.Tensor, shifts: int, split: bool, overlap: f
 def apply_model_oracle(models, mix: torch.Tensor, shifts: int = 1, split: bool = True,
                        overlap: float = 0.25, transition_power: float = 1.0,
                        segment: tp.Optional[float] = None,
-                       bag_weights: tp.Optional[tp.List[tp.List[float]]] = None) -> torch.Tensor:
-    """``models``: a (weights, cfg) pair or a list of them (a bag, apply.py:201-229)."""
+                       bag_weights: tp.Optional[tp.List[tp.List[float]]] = None,
+                       window: tp.Optional[tp.Tuple[int, int]] = None) -> torch.Tensor:
+    """``models``: a (weights, cfg) pair or a list of them (a bag, apply.py:201-229).  ``window``: see apply_single."""
     if isinstance(models, tuple):
         W, cfg = models
-        return apply_single(W, cfg, mix, shifts, split, overlap, transition_power, segment)
+        return apply_single(W, cfg, mix, shifts, split, overlap, transition_power, segment, window=window)
     S = models[0][1].n_sources
     if bag_weights is None:
         bag_weights = [[1.0] * S for _ in models]
     totals = [0.0] * S
     est = 0.0
     for (W, cfg), mw in zip(models, bag_weights):
-        out = apply_single(W, cfg, mix, shifts, split, overlap, transition_power, segment)
+        out = apply_single(W, cfg, mix, shifts, split, overlap, transition_power, segment, window=window)
         for k, w in enumerate(mw):
             out[:, k] *= w
             totals[k] += w
