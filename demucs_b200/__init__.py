@@ -10,6 +10,7 @@ from .weights import init_weights, param_specs, count_params  # noqa
 from .htdemucs import HTDemucs, htdemucs  # noqa
 from .apply import apply_model, BagOfModels, TensorChunk, tensor_chunk, center_trim  # noqa
 from .api import Separator, LoadAudioError, LoadModelError, list_models  # noqa
+from .repo import get_model, load_model, ModelLoadingError  # noqa
 from ._lib import KernelError  # noqa
 
 __version__ = "0.1.0"

@@ -1,11 +1,14 @@
 """``Separator`` -- user-facing front door (drop-in for reference demucs/api.py:53-319).
 
 Keeps the reference's constructor, ``update_parameter``, ``separate_tensor`` and the
-``samplerate / audio_channels / model`` properties.  Two things the reference does through
-absent third-party code are out of the accelerated path:
-the pretrained-model zoo (needs the network) and ffmpeg/torchaudio file decoding.  A model is
-therefore passed in as an object (``HTDemucs`` / ``BagOfModels``) or named among the built-in
-synthetic architectures, and ``separate_audio_file`` needs ``torchaudio`` able to read the file.
+``samplerate / audio_channels / model`` properties.  A model name / signature is resolved as in the
+reference (``demucs_b200.repo.get_model``: a local ``repo`` folder of ``.th`` packages and bag YAML files,
+or the remote zoo as far as torch hub has it cached -- there is no network here); ``"synthetic:<name>"``
+names the random-init stand-ins of the released architectures, and a model object can be passed directly.
+Audio that is not at the model's sample rate / channel count is converted on the device
+(``demucs_b200.audio.convert_audio``, the julius-equivalent polyphase resampler), and
+``separate_tensor_pcm`` / ``demucs_b200.audio.save_audio`` take the stems off the GPU in wire format
+(clip prevention + PCM quantisation as device kernels).  File decoding still needs ``torchaudio``.
 """
 from __future__ import annotations
 
@@ -36,7 +39,7 @@ SOURCES_4 = ["drums", "bass", "other", "vocals"]
 
 
 def _builtin(name: str):
-    """Random-init stand-ins for the released checkpoints (remote/*.yaml), which need the network."""
+    """Random-init stand-ins for the released checkpoints (remote/*.yaml): ``synthetic:<name>``."""
     if name == "htdemucs":
         return htdemucs(SOURCES_4)
     if name == "htdemucs_6s":
@@ -49,8 +52,11 @@ def _builtin(name: str):
 
 
 def list_models(repo: Optional[Path] = None) -> Dict[str, Dict[str, Union[str, Path]]]:
-    """Reference api.py:322-346; only the built-in synthetic architectures exist offline."""
-    return {"single": {"htdemucs": "builtin", "htdemucs_6s": "builtin"}, "bag": {"htdemucs_ft": "builtin"}}
+    """Reference api.py:322-346: the single models and the bags of a repo (default: the HTDemucs part of the remote zoo)."""
+    from .repo import RemoteRepo, LocalRepo, BagOnlyRepo
+    model_repo = RemoteRepo() if repo is None else LocalRepo(Path(repo))
+    bag_repo = BagOnlyRepo(None if repo is None else Path(repo), model_repo)
+    return {"single": dict(model_repo.list_model()), "bag": dict(bag_repo.list_model())}
 
 
 class Separator:
@@ -90,8 +96,14 @@ class Separator:
     def _load_model(self):
         if isinstance(self._name, (HTDemucs, BagOfModels)):
             self._model = self._name
+        elif isinstance(self._name, str) and self._name.startswith("synthetic:"):
+            self._model = _builtin(self._name[len("synthetic:"):])
         else:
-            self._model = _builtin(self._name)
+            from .repo import get_model, ModelLoadingError
+            try:
+                self._model = get_model(name=self._name, repo=self._repo)      # api.py:199-201
+            except ModelLoadingError as err:
+                raise LoadModelError(f"Failed to load model: {err}") from err
         if self._model is None:
             raise LoadModelError("Failed to load model")
         self._audio_channels = self._model.audio_channels
