@@ -465,7 +465,24 @@ class Engine:
             self._bufs.clear()
             raise
 
-    def _forward(self, mix: torch.Tensor, taps: tp.Optional[dict], out_buf: tp.Optional[torch.Tensor]) -> torch.Tensor:
+    @torch.no_grad()
+    def forward_core(self, mag: torch.Tensor, mix: torch.Tensor) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+        """The network between the STFT and the iSTFT (reference ``HTDemucs.forward_core``, htdemucs.py:662-759, its
+        ONNX-export surface): mag [B, 2*audio_channels, 2048, T] = ``_magnitude(_spec(mix))`` (any tensor of that
+        shape is accepted, as in the reference), mix [B, audio_channels, L = training length] ->
+        (spec_out [B, S, 2*audio_channels, 2048, T], time_out [B, S, audio_channels, L]), both de-normalised.
+        The layout changes at this boundary (NCHW in and out) are plain copies; everything between runs in the
+        same kernels as ``forward``."""
+        try:
+            if self.device.type == "cuda":
+                with torch.cuda.device(self.device):
+                    return self._forward(mix, None, None, mag=mag)
+            return self._forward(mix, None, None, mag=mag)
+        except BaseException:
+            self._bufs.clear()
+            raise
+
+    def _forward(self, mix: torch.Tensor, taps: tp.Optional[dict], out_buf: tp.Optional[torch.Tensor], mag=None):
         cfg, W = self.cfg, self.W
         if mix.dim() != 3 or mix.shape[1] != cfg.audio_channels:
             raise ValueError(f"expected mix of shape [B, {cfg.audio_channels}, L], got {tuple(mix.shape)}")
@@ -503,8 +520,20 @@ class Engine:
         stats = self._buf(key, "item_stats", 4 * B, torch.float64)
         norm = self._buf(key, "item_norm", 8 * B)
         stats.zero_()
-        self._k("bd_stft_cac", ptr(mix), ptr(self.window), ptr(self.twiddle), ptr(spec), ptr(stats), B, A, L, st,
-                nbytes=4.0 * B * (A * L + T * 2048 * 4), flops=2.5 * 4096 * 12 * 2 * B * T)
+        if mag is None:
+            self._k("bd_stft_cac", ptr(mix), ptr(self.window), ptr(self.twiddle), ptr(spec), ptr(stats), B, A, L, st,
+                    nbytes=4.0 * B * (A * L + T * 2048 * 4), flops=2.5 * 4096 * 12 * 2 * B * T)
+        else:       # forward_core: the spectrogram is given; only its statistics (and the mix's) are computed here
+            if L0 != L or tuple(mag.shape) != (B, 2 * A, 2048, T) or mag.device != self.device or mag.dtype != torch.float32:
+                raise ValueError(f"forward_core expects mag [B, {2 * A}, 2048, {T}] and mix [B, {A}, {L}] (float32, on "
+                                 f"the engine's device), got {tuple(mag.shape)} and {tuple(mix.shape)}")
+            spec.view(B, T, 2048, 2 * A).copy_(mag.permute(0, 3, 2, 1))
+            pair = self._buf(key, "core_stats", 4 * B, torch.float64)
+            pair.zero_()
+            self._k("bd_item_stats", ptr(spec), ptr(pair), B, 2 * A * 2048 * T, st, nbytes=4.0 * spec.numel())
+            self._k("bd_item_stats", ptr(mix), pair.data_ptr() + 16 * B, B, A * L, st, nbytes=4.0 * mix.numel())
+            stats.view(B, 4)[:, :2].copy_(pair[:2 * B].view(B, 2))
+            stats.view(B, 4)[:, 2:].copy_(pair[2 * B:].view(B, 2))
         self._k("bd_finalize_item_norm", ptr(stats), ptr(norm), B, float(4 * 2048 * T), float(A * L), st)
         tap("stft", spec.view(B, T, 2048, 4), "f")
 
@@ -689,6 +718,14 @@ class Engine:
                 tap(f"tdec{j}", (nxt - skip_t if skip_t is not None else nxt).view(B, tp(Tout), Cout_t)[:, :Tout], "t")
             xtd = nxt
 
+        if mag is not None:
+            # forward_core: hand back both branches de-normalised (htdemucs.py:751-757), in the reference's layouts
+            nm = norm.view(B, 8)
+            spec_out = xd[: B * T * S * 2048 * 2 * A].view(B, T, S, 2048, 2 * A).permute(0, 2, 4, 3, 1)
+            spec_out = spec_out * nm[:, 1].view(B, 1, 1, 1, 1) + nm[:, 0].view(B, 1, 1, 1, 1)
+            time_out = xtd[: B * tp(L) * A * S].view(B, tp(L), S, A)[:, :L].permute(0, 2, 3, 1)
+            time_out = time_out * nm[:, 5].view(B, 1, 1, 1) + nm[:, 4].view(B, 1, 1, 1)
+            return spec_out.contiguous(), time_out.contiguous()
         # ---- K2: de-normalise, iSTFT, overlap-add in shared memory, crop, add the time branch ------------
         if out_buf is not None:
             if out_buf.numel() != B * S * A * L0 or out_buf.dtype != torch.float32 or out_buf.device != self.device \

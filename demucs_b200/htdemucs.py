@@ -135,6 +135,11 @@ class HTDemucs(nn.Module):
         (htdemucs.py:527-660).  ``mix`` must live on the same CUDA device as the parameters."""
         return self.engine().forward(mix.float())
 
+    def forward_core(self, mag: torch.Tensor, mix: torch.Tensor) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+        """htdemucs.py:662-759 (the ONNX-export surface): mag [B, 2C, F, T] = ``_magnitude(_spec(mix))``,
+        mix [B, C, L = training length] -> (spec_out [B, S, 2C, F, T], time_out [B, S, C, L])."""
+        return self.engine().forward_core(mag.float(), mix.float())
+
     def extra_repr(self) -> str:
         return f"sources={self.sources}, segment={float(self.segment):.2f}s, mode={self.mode}"
 

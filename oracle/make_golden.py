@@ -146,6 +146,24 @@ def spectral_fixture():
     print("spectral", {k: v.shape for k, v in data.items()})
 
 
+def core_fixture():
+    """``HTDemucs.forward_core`` of the reference (htdemucs.py:662-759) on the small geometry; the spectrogram handed in
+    is the mixture's own plus noise, so that the result depends on the ``mag`` argument and not on a recomputed STFT."""
+    cfg = small_config()
+    W = init_weights(cfg, 0, layer_scale=0.5)
+    model = refload.build_reference_model(cfg, W)
+    mix = synth_mix(2, cfg.segment_length, 1240)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        mag = model._magnitude(model._spec(mix))
+        mag = mag + 0.05 * mag.std() * torch.randn(mag.shape, generator=g)
+        spec_out, time_out = model.forward_core(mag, mix)
+    data = {"spec_out": sample(spec_out, 211), "time_out": sample(time_out, 7), "spec_shape": np.array(spec_out.shape),
+            "time_shape": np.array(time_out.shape), "mag": sample(mag, 211)}
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "core_small.npz"), **data)
+    print("core_small", {k: v.shape for k, v in data.items()})
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
@@ -157,6 +175,7 @@ def main():
     forward_fixture("htdemucs_default.npz", full, 0, None, 1, full.segment_length, 29, 4999)
     forward_fixture("htdemucs_ls05.npz", full, 0, 0.5, 1, full.segment_length, 29, 4999)
     apply_fixture()
+    core_fixture()
 
 
 if __name__ == "__main__":

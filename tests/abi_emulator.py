@@ -282,6 +282,13 @@ def bd_layer_norm(x, y, gamma, beta, pos, period, M, Cc, y_bf16, stream):
     f32(y, M * Cc)[:] = o.astype(np.float32).reshape(-1)
 
 
+def bd_item_stats(x, sums, B, n, stream):
+    v = f32(x, B * n).reshape(B, n).astype(np.float64)
+    st = f64(sums, 2 * B).reshape(B, 2)
+    st[:, 0] += v.sum(1)
+    st[:, 1] += (v ** 2).sum(1)
+
+
 def bd_group_norm_apply(x, mr, gamma, beta, B, rows, Cc, stream):
     xv = f32(x, B * rows * Cc).reshape(B, rows, Cc)
     st = f32(mr, 2 * B).reshape(B, 2)

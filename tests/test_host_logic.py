@@ -156,3 +156,23 @@ def test_engine_tf32_host_paths_with_48_channels():
         calls = set(E.CALLS)
     assert {"bd_encoder_conv0", "bd_dconv_conv3", "bd_dconv_expand_stats", "bd_dconv_expand_update"} <= calls
     assert rel_l2(got, want) < 1e-5
+
+
+def test_forward_core_matches_reference_golden():
+    """HTDemucs.forward_core (htdemucs.py:662-759, the ONNX-export surface) through the engine's host logic."""
+    g = golden("core_small.npz")
+    cfg = small_config()
+    model = D.HTDemucs.from_config(cfg, init_seed=0, layer_scale=0.5, mode="fp32")
+    mix = synth_mix(2, cfg.segment_length, 1240)
+    from oracle.htdemucs_oracle import stft_cac
+    gen = torch.Generator().manual_seed(5)
+    mag = stft_cac(mix, cfg.nfft)
+    mag = mag + 0.05 * mag.std() * torch.randn(mag.shape, generator=gen)
+    assert rel_l2(strided(mag, 211), g["mag"]) < 1e-5
+    with emulated_abi():
+        spec_out, time_out = model.forward_core(mag, mix)
+    assert list(spec_out.shape) == list(g["spec_shape"]) and list(time_out.shape) == list(g["time_shape"])
+    assert rel_l2(strided(spec_out, 211), g["spec_out"]) < 1e-5
+    assert rel_l2(strided(time_out, 7), g["time_out"]) < 1e-5
+    with emulated_abi(), pytest.raises(ValueError):
+        model.forward_core(mag[..., :-1], mix)
