@@ -115,16 +115,18 @@ class Separator:
             wav, sr = ta.load(str(track))
         except Exception as err:  # noqa
             raise LoadAudioError(f"When trying to load using torchaudio, got the following error: {err}")
-        if sr != self._samplerate or wav.shape[0] != self._audio_channels:
-            raise LoadAudioError("resampling / channel conversion (julius) is outside the accelerated path")
+        if sr != self._samplerate or wav.shape[0] != self._audio_channels:      # api.py:221: convert_audio, on the device
+            from .audio import convert_audio
+            wav = convert_audio(wav.to(self._device), sr, self._samplerate, self._audio_channels).cpu()
         return wav
 
     def separate_tensor(self, wav: th.Tensor, sr: Optional[int] = None) -> Tuple[th.Tensor, Dict[str, th.Tensor]]:
         """Reference api.py:241-291: normalise by the mono mean/std, separate, de-normalise.
         ``wav`` [channels, length] float32 is modified in place and restored, as in the reference."""
-        if sr is not None and sr != self.samplerate:
-            raise LoadAudioError("resampling (julius) is outside the accelerated path; pass audio at "
-                                 f"{self.samplerate} Hz")
+        home = wav.device
+        if sr is not None and sr != self.samplerate:        # api.py:265-266, as a device kernel
+            from .audio import convert_audio
+            wav = convert_audio(wav.to(self._device), sr, self._samplerate, self._audio_channels).to(home)
         ref = wav.mean(0)
         wav -= ref.mean()
         wav /= ref.std() + 1e-8
@@ -148,6 +150,17 @@ class Separator:
         wav *= ref.std() + 1e-8
         wav += ref.mean()
         return (wav, dict(zip(self._model.sources, out[0])))
+
+    def separate_tensor_pcm(self, wav: th.Tensor, sr: Optional[int] = None, clip: Optional[str] = "rescale",
+                            bits_per_sample: int = 16, as_float: bool = False) -> Dict[str, th.Tensor]:
+        """``separate_tensor`` with the back door of ``save_audio`` (audio.py:236-265) attached, device-resident end to
+        end: the wave is converted / normalised / separated on the GPU and every stem leaves it as interleaved PCM
+        frames [frames, channels] (int16, 24-bit in int32, or float32) in pinned host memory -- clip prevention and
+        quantisation are device kernels, so a 16-bit stem costs half the PCIe bytes of a float one."""
+        from .audio import stems_to_pcm
+        dev_wav = wav.to(self._device, copy=True)
+        _, stems = self.separate_tensor(dev_wav, sr)
+        return {name: stems_to_pcm(stem, clip, bits_per_sample, as_float) for name, stem in stems.items()}
 
     def separate_audio_file(self, file: Path):
         return self.separate_tensor(self._load_audio(file), self.samplerate)

@@ -215,6 +215,26 @@ int bd_gather_segments(const float* track, float* batch, int B, int C, long long
                        long long length, int seg_first, int nseg_batch, int seg_len, int stride, int valid,
                        void* stream);
 
+/* ---- front / back door of the separator (api.py:265-266, audio.py:143-172,175-265) ------------------------------
+ * Channel conversion (audio.py:143-166) of x [items, src_ch, len] -> y [items, dst_ch, len]: copy, downmix to mono,
+ * replicate mono, or keep the first dst_ch channels. */
+int bd_convert_channels(const float* x, float* y, int items, int src_ch, int dst_ch, long long len, void* stream);
+/* convert_audio (audio.py:169-172): channel conversion + julius.resample_frac(old_sr -> new_sr) in one pass.
+ * old_sr / new_sr are the rates divided by their gcd; kernel [new_sr, 2*width + old_sr] is the windowed-sinc filter
+ * bank (demucs_b200/audio.py builds it as julius 0.2.x does: zeros 24, rolloff 0.945, each phase normalised to unit
+ * sum); the input is edge-replicated by `width` samples on the left and width + old_sr on the right;
+ * Lout <= ceil(Lin*new_sr/old_sr) (julius' default is the floor). */
+int bd_resample_frac(const float* x, float* y, const float* kernel, int items, int src_ch, int dst_ch, long long Lin,
+                     long long Lout, int old_sr, int new_sr, int width, void* stream);
+/* peak[0] = max |x| over n samples (for prevent_clip's rescale mode, audio.py:223-224). */
+int bd_absmax(const float* x, float* peak, long long n, void* stream);
+/* prevent_clip (audio.py:218-233) + PCM quantisation (i16_pcm, audio.py:175-180) + planar -> interleaved:
+ * x [channels, frames] -> out [frames, channels] as int16 (bits 16: clamp to [-1,1], * 32767, truncate), int32 holding
+ * a 24-bit value (bits 24, * 8388607) or float (bits 32).  mode: BD_CLIP_*; rescale divides by max(1.01*peak, 1). */
+enum { BD_CLIP_NONE = 0, BD_CLIP_RESCALE = 1, BD_CLIP_CLAMP = 2, BD_CLIP_TANH = 3 };
+int bd_clip_pcm(const float* x, void* out, int channels, long long frames, int mode, const float* peak, int bits,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,6 +164,30 @@ def core_fixture():
     print("core_small", {k: v.shape for k, v in data.items()})
 
 
+def audio_fixture():
+    """The reference's own ``convert_audio_channels`` / ``prevent_clip`` / ``i16_pcm`` (audio.py:143-166,175-180,218-233;
+    lameenc is stubbed: it only serves mp3 encoding) on fixed inputs."""
+    import sys
+    import types
+    refload.load()
+    sys.modules.setdefault("lameenc", types.ModuleType("lameenc"))
+    import demucs.audio as ra
+    g = torch.Generator().manual_seed(21)
+    data = {}
+    x5 = torch.randn(3, 5, 1000, generator=g)
+    data["ch_5to2"] = ra.convert_audio_channels(x5, 2).contiguous().numpy()
+    data["ch_5to1"] = ra.convert_audio_channels(x5, 1).contiguous().numpy()
+    data["ch_1to2"] = ra.convert_audio_channels(x5[:, :1], 2).contiguous().numpy()
+    loud = 1.7 * torch.randn(2, 5000, generator=g)
+    quiet = 0.2 * torch.randn(2, 5000, generator=g)
+    for mode in ("rescale", "clamp", "tanh"):
+        data[f"clip_{mode}_loud"] = ra.prevent_clip(loud.clone(), mode).numpy()
+        data[f"clip_{mode}_quiet"] = ra.prevent_clip(quiet.clone(), mode).numpy()
+    data["i16_loud"] = ra.i16_pcm(loud.clone()).numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "audio.npz"), **data)
+    print("audio", {k: v.shape for k, v in data.items()})
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
@@ -176,6 +200,7 @@ def main():
     forward_fixture("htdemucs_ls05.npz", full, 0, 0.5, 1, full.segment_length, 29, 4999)
     apply_fixture()
     core_fixture()
+    audio_fixture()
 
 
 if __name__ == "__main__":

@@ -359,6 +359,55 @@ def bd_gather_segments(track, batch, B, Cc, track_len, offset0, length, seg_firs
             out[j][:, lo - start:hi - start] = tr[:, lo:hi]
 
 
+def _mix_channels(x, src, dst):
+    if src == dst or (src > dst and dst != 1):
+        return x[:, :dst]
+    if src == 1:
+        return np.repeat(x, dst, axis=1)
+    return x.mean(axis=1, keepdims=True).astype(np.float32)
+
+
+def bd_convert_channels(x, y, items, src, dst, length, stream):
+    f32(y, items * dst * length).reshape(items, dst, length)[:] = _mix_channels(
+        f32(x, items * src * length).reshape(items, src, length), src, dst)
+
+
+def bd_resample_frac(x, y, kernel, items, src, dst, Lin, Lout, old_sr, new_sr, width, stream):
+    xin = _mix_channels(f32(x, items * src * Lin).reshape(items, src, Lin), src, dst)
+    klen = 2 * width + old_sr
+    k = f32(kernel, new_sr * klen).reshape(new_sr, klen)
+    out = f32(y, items * dst * Lout).reshape(items, dst, Lout)
+    o = np.arange(Lout)
+    j, i = o // new_sr, o % new_sr
+    idx = np.clip(j[:, None] * old_sr - width + np.arange(klen)[None, :], 0, Lin - 1)
+    out[:] = np.einsum("bcok,ok->bco", xin[:, :, idx], k[i]).astype(np.float32)
+
+
+def bd_absmax(x, peak, n, stream):
+    f32(peak, 1)[0] = np.abs(f32(x, n)).max()
+
+
+def bd_clip_pcm(x, out, channels, frames, mode, peak, bits, stream):
+    v = f32(x, channels * frames).reshape(channels, frames).copy()
+    if mode == 1:
+        v = v * (np.float32(1.0) / max(np.float32(1.01) * f32(peak, 1)[0], np.float32(1.0)))
+    elif mode == 2:
+        v = np.clip(v, -0.99, 0.99)
+    elif mode == 3:
+        v = np.tanh(v)
+    v = v.T
+    if bits == 32:
+        f32(out, channels * frames).reshape(frames, channels)[:] = v
+        return
+    v = np.clip(v, -1, 1)
+    if bits == 16:
+        dst = np.ctypeslib.as_array(C.cast(C.c_void_p(out), C.POINTER(C.c_int16)), shape=(frames * channels,))
+        dst.reshape(frames, channels)[:] = np.trunc(v * np.float32(32767.0)).astype(np.int16)
+    else:
+        dst = np.ctypeslib.as_array(C.cast(C.c_void_p(out), C.POINTER(C.c_int32)), shape=(frames * channels,))
+        dst.reshape(frames, channels)[:] = np.trunc(v * np.float32(8388607.0)).astype(np.int32)
+
+
 TABLE = {k: v for k, v in globals().items() if k.startswith("bd_")}
 CALLS = []
 
