@@ -135,8 +135,14 @@ def init_weights(cfg: HTDemucsConfig, seed: int = 0, layer_scale: tp.Optional[fl
     followed by ``rescale_module`` for the convolutions, htdemucs.py:365-366), and the
     affine norm parameters are perturbed away from (1, 0) so that they are exercised.
     """
+    return init_from_specs(param_specs(cfg), seed, layer_scale, cfg.emb_scale, dtype)
+
+
+def init_from_specs(specs, seed: int = 0, layer_scale: tp.Optional[float] = None, emb_scale: float = 10.0,
+                    dtype=torch.float32) -> "collections.OrderedDict[str, torch.Tensor]":
+    """Synthetic values for a name -> (shape, kind, hint) inventory (HTDemucs and HDemucs share the generator)."""
     out = collections.OrderedDict()
-    for name, (shape, kind, hint) in param_specs(cfg).items():
+    for name, (shape, kind, hint) in specs.items():
         key = zlib.crc32(name.encode()) & 0xFFFFFFFF
         rng = np.random.Generator(np.random.PCG64([seed, key]))
         if kind in ("conv", "linear", "bias"):
@@ -145,6 +151,13 @@ def init_weights(cfg: HTDemucsConfig, seed: int = 0, layer_scale: tp.Optional[fl
                 std = bound / np.sqrt(3.0)
                 bound = bound / np.sqrt(std / 0.1)  # rescale_module, demucs.py:69-77
             w = rng.uniform(-bound, bound, size=shape)
+        elif kind == "lstm":          # nn.LSTM.reset_parameters: U(-1/sqrt(hidden), 1/sqrt(hidden))
+            bound = 1.0 / np.sqrt(float(hint))
+            w = rng.uniform(-bound, bound, size=shape)
+        elif kind == "decay_w":       # LocalState.query_decay (demucs.py:181-184): weight * 0.01 ...
+            w = 0.01 * rng.uniform(-1, 1, size=shape) / np.sqrt(float(hint))
+        elif kind == "decay_b":       # ... bias = -2; perturbed so that the four decay rates differ
+            w = -2.0 + 0.5 * rng.standard_normal(shape)
         elif kind == "norm_w":
             w = 1.0 + 0.2 * rng.standard_normal(shape)
         elif kind == "norm_b":
@@ -155,7 +168,7 @@ def init_weights(cfg: HTDemucsConfig, seed: int = 0, layer_scale: tp.Optional[fl
         elif kind == "emb":
             # smooth cumulative-sum embedding divided by emb_scale (hdemucs.py:52-58)
             w = np.cumsum(rng.standard_normal(shape), axis=0)
-            w = w / np.sqrt(np.arange(1, shape[0] + 1))[:, None] / cfg.emb_scale
+            w = w / np.sqrt(np.arange(1, shape[0] + 1))[:, None] / emb_scale
         else:  # pragma: no cover
             raise AssertionError(kind)
         out[name] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).to(dtype)

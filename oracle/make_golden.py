@@ -164,6 +164,55 @@ def core_fixture():
     print("core_small", {k: v.shape for k, v in data.items()})
 
 
+def hdemucs_reference(cfg, W):
+    refload.load()
+    import demucs.hdemucs as H
+    model = H.HDemucs(**cfg.reference_kwargs()).eval()
+    model.load_state_dict({k: v.float() for k, v in W.items()}, strict=True)
+    return model
+
+
+def hdemucs_fixture(name, cfg, seed, layer_scale, batch, length, stride, tap_stride):
+    """``HDemucs.forward`` of the reference (hdemucs.py:689-794) with hooks on every encoder / decoder layer."""
+    from demucs_b200.hdemucs import init_weights as h_init
+    W = h_init(cfg, seed, layer_scale)
+    model = hdemucs_reference(cfg, W)
+    mix = synth_mix(batch, length, 4321 + seed)
+    taps, hooks = {}, []
+
+    def grab(key, fn=lambda o: o):
+        def hook(_m, _i, o):
+            taps[key] = fn(o).detach()
+        return hook
+    for i in range(len(model.encoder)):
+        hooks.append(model.encoder[i].register_forward_hook(grab(f"enc{i}")))
+        hooks.append(model.decoder[i].register_forward_hook(grab(f"dec{i}", lambda o: o[0])))
+    for i in range(len(model.tencoder)):
+        hooks.append(model.tencoder[i].register_forward_hook(grab(f"tenc{i}")))
+        hooks.append(model.tdecoder[i].register_forward_hook(grab(f"tdec{i}", lambda o: o[0])))
+    with torch.no_grad():
+        out = model(mix)
+        frs = torch.arange(taps["enc0"].shape[-2])
+        taps["enc0"] = taps["enc0"] + model.freq_emb_scale * model.freq_emb(frs).t()[None, :, :, None]
+    for h in hooks:
+        h.remove()
+    data = {"out": sample(out, stride), "stride": stride, "tap_stride": tap_stride, "seed": seed,
+            "layer_scale": -1.0 if layer_scale is None else layer_scale, "batch": batch, "length": length,
+            "out_shape": np.array(out.shape), "names": np.array(list(W)), "shapes": np.array([str(tuple(v.shape)) for v in W.values()])}
+    for k, v in taps.items():
+        data[f"tap.{k}"] = sample(v, tap_stride)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), **data)
+    print(name, data["out"].shape, len(taps), "taps")
+
+
+def hdemucs_small_config():
+    """The hdemucs_mmi topology (6 layers, GroupNorm / BLSTM / LocalState from layer 4, inject at layer 4), thin."""
+    from demucs_b200.hdemucs import HDemucsConfig
+    cfg = HDemucsConfig(sources=["a", "b", "c"], channels=16, dconv_comp=4, dconv_init=1e-3, segment=3)
+    cfg.validate()
+    return cfg
+
+
 def audio_fixture():
     """The reference's own ``convert_audio_channels`` / ``prevent_clip`` / ``i16_pcm`` (audio.py:143-166,175-180,218-233;
     lameenc is stubbed: it only serves mp3 encoding) on fixed inputs."""
@@ -201,6 +250,10 @@ def main():
     apply_fixture()
     core_fixture()
     audio_fixture()
+    from demucs_b200.hdemucs import hdemucs_mmi_config
+    hdemucs_fixture("hdemucs_small.npz", hdemucs_small_config(), 0, 0.5, 2, 343980, 13, 211)
+    hdemucs_fixture("hdemucs_small_odd.npz", hdemucs_small_config(), 1, 0.5, 1, 100001, 13, 211)
+    hdemucs_fixture("hdemucs_mmi.npz", hdemucs_mmi_config(), 0, 0.5, 1, 343980, 29, 4999)
 
 
 if __name__ == "__main__":
