@@ -405,13 +405,98 @@ def gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
+def hdemucs_arm(args) -> None:
+    """BASELINE configs[1]: the hdemucs_mmi architecture (Hybrid Demucs v3, 83.6 M parameters, no transformer), forward of
+    a batch of 16 x 7.8 s segments on one B200.  value: audio-seconds per second with the batch resident in HBM; e2e: the
+    same from pinned host memory and back; parity: one item against the CPU oracle."""
+    import torch
+    from demucs_b200 import hdemucs as HD, perf
+    from demucs_b200.hdemucs_engine import HDemucsEngine
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    cfg = HD.hdemucs_mmi_config()
+    W = HD.init_weights(cfg, 0)
+    mode = args.mode or "strict"
+    eng = HDemucsEngine(cfg, W, dev, mode=mode)
+    B, L = 16, SEG_LEN
+    host = (0.1 * torch.randn(B, 2, L, generator=torch.Generator().manual_seed(1234))).pin_memory()
+    x = host.to(dev)
+    out = torch.empty(B, 4, 2, L, device=dev)
+    host_out = torch.empty(B, 4, 2, L).pin_memory()
+
+    def step():
+        eng.forward(x, out=out)
+
+    def step_e2e():
+        xd = host.to(dev, non_blocking=True)
+        eng.forward(xd, out=out)
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(0)
+    l0 = eng.launches
+    ms = timed(step, args.steps)
+    launches = eng.launches - l0
+    clocks = sampler.stop()
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    prof = perf.profile_step(eng, step)
+    peaks = measured_peaks()
+    top = prof["dominant"]
+    if top["bound"] == "tensor":
+        achieved, peak, unit = top["tflops"], peaks["bf16_tflops"], "TFLOP/s"
+    else:
+        achieved, peak, unit = top["gbs"], peaks["hbm_gbs"], "GB/s"
+    parity = cpu_baseline = None
+    if not args.no_cpu:
+        from oracle.hdemucs_oracle import hdemucs_forward
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            hdemucs_forward(W, cfg, host[:1])
+            t0 = time.perf_counter()
+            want = hdemucs_forward(W, cfg, host[:2])
+            sec = time.perf_counter() - t0
+        got = eng.forward(x[:2].contiguous()).cpu()
+        err = max(float((got[:, s_] - want[:, s_]).norm() / want[:, s_].norm()) for s_ in range(4))
+        parity = {"against": "port (oracle)", "clip": "items 0-1 of the batch", "mode": mode, "per_stem_rel_l2_max": err,
+                  "tolerance": TOLERANCE[mode], "within_tolerance": err <= TOLERANCE[mode] if TOLERANCE[mode] else None}
+        cpu_baseline = {"value": 2 * L / SR / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"one forward of 2 x 7.8 s items after a warm-up, torch {torch.__version__} CPU fp32"}
+    audio_s = B * L / SR
+    line = {"metric": "hdemucs_mmi audio-seconds separated per second (forward of 16 x 7.8 s)", "value": audio_s / (ms / 1e3),
+            "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[mode], "data": "synthetic",
+            "config": {"workload": "hdemucs_mmi architecture (Hybrid Demucs v3, random-init, 83.6 M parameters): STFT + dual U-Net "
+                                   "forward, batch 16 x 7.8 s segments on 1 B200 (BASELINE configs[1])", "name": "hdemucs_mmi",
+                       "mode": mode, "l2": "activations of a step exceed L2 many times over"},
+            "e2e": {"value": audio_s / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": host.numel() * 4,
+                    "d2h_bytes_per_step": host_out.numel() * 4, "api": "HDemucsEngine.forward on a pinned host batch"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"kernel": top["name"], "bound": top["bound"], "achieved": achieved, "peak": peak, "unit": unit,
+                         "frac": achieved / peak, "traffic": None, "share_of_step": top["share"], "kernels": prof["table"]},
+            "cpu_baseline": cpu_baseline, "parity": parity}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="configs2", choices=list(WORKLOADS),
+    ap.add_argument("--config", default="configs2", choices=list(WORKLOADS) + ["hdemucs_mmi"],
                     help="configs2 (default, the headline): 64 x 7.8 s segments; 6s_10min / ft_10min: BASELINE configs[3] / [4]")
     ap.add_argument("--mode", default=os.environ.get("BD_MODE"), choices=["fp32", "tf32", "tf32x3", "strict", "bf16"],
                     help="strict (default): error-compensated tensor-core arithmetic, per-stem rel-L2 <= 1e-4; "
@@ -420,8 +505,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion run")
     args = ap.parse_args()
+    if args.config == "hdemucs_mmi" and args.impl != "reference":
+        return hdemucs_arm(args)
     if args.mode is None:
-        args.mode = WORKLOADS[args.config][3]
+        args.mode = WORKLOADS.get(args.config, WORKLOADS["configs2"])[3]
     if args.impl == "reference":
         reference_arm(args)
     else:

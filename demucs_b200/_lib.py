@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdemucs_b200.so")
 SOURCES = ["api.cu", "spectral.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_b16x3.cu", "gemm_tc_b16.cu", "norm.cu", "dconv.cu", "attention.cu", "attention_tc.cu", "attention_b16.cu",
-           "ola.cu", "audio.cu"]
+           "ola.cu", "audio.cu", "hdemucs.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -74,6 +74,12 @@ SIGNATURES: tp.Dict[str, tp.List] = {
     "bd_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "bd_overlap_add": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _LL, _LL, _LL, _LL, _LL, _P, _F, _I, _P],
     "bd_gather_segments": [_P, _P, _I, _I, _LL, _LL, _LL, _I, _I, _I, _I, _I, _P],
+    "bd_gn_stats": [_P, _P, _I, _LL, _I, _I, _P],
+    "bd_gn_act": [_P, _P, _P, _P, _P, _P, _I, _LL, _LL, _LL, _I, _I, _I, _LL, _P],
+    "bd_lstm_frame": [_P, _P, _I, _LL, _I, _I, _I, _I, _P],
+    "bd_lstm_unframe_add": [_P, _P, _P, _I, _LL, _I, _I, _I, _I, _P],
+    "bd_lstm_bidir": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "bd_local_state": [_P, _P, _P, _I, _I, _I, _I, _P],
     "bd_convert_channels": [_P, _P, _I, _I, _I, _LL, _P],
     "bd_resample_frac": [_P, _P, _P, _I, _I, _I, _LL, _LL, _I, _I, _I, _P],
     "bd_absmax": [_P, _P, _LL, _P],

@@ -67,6 +67,69 @@ def _sin_embedding_2d(dim: int, height: int, width: int, max_period: float) -> t
     return pe.reshape(width * height, dim)
 
 
+def conv_w(w):
+    """[Cout, Cin, k(,1)] / [Cout, Cin, kf, kt] -> [Cout, taps*Cin], tap-major."""
+    w = w.detach().float()
+    co, ci = w.shape[:2]
+    return w.reshape(co, ci, -1).permute(0, 2, 1).reshape(co, -1)
+
+
+def convtr_w(w):
+    """[Cin, Cout, 8(,1)] -> [4*Cout, 2*Cin]; row r*Cout+co, col tap*Cin+ci = w[ci,co,r+4tap]."""
+    w = w.detach().float()
+    ci, co = w.shape[:2]
+    w = w.reshape(ci, co, 2, 4)                 # k = 4*tap + r
+    return w.permute(3, 1, 2, 0).reshape(4 * co, 2 * ci)
+
+
+def convtr_w3(w):
+    """3-tap form of the same transposed conv: output row p = 4 outputs 4p+s, s<4, read x[p-1], x[p], x[p+1]:
+    u = 4p+s+2 = 4*ti + k  =>  tap -1: k=s+6 (s<=1), tap 0: k=s+2, tap +1: k=s-2 (s>=2); other entries zero.
+    Rows = input positions exactly, so tensor-core tiles carry no halo row."""
+    w = w.detach().float()
+    ci, co = w.shape[:2]
+    w = w.reshape(ci, co, 8)
+    out = torch.zeros(4, co, 3, ci)
+    for s_ in range(4):
+        out[s_, :, 1] = w[:, :, s_ + 2].t()
+        if s_ <= 1:
+            out[s_, :, 0] = w[:, :, s_ + 6].t()
+        else:
+            out[s_, :, 2] = w[:, :, s_ - 2].t()
+    return out.reshape(4 * co, 3 * ci)
+
+
+def pack_dconv(put, packed, state, prefix: str, depth: int, tc_forms: bool, idx=(0, 1, 3, 4, 6)) -> None:
+    """DConv parameters of ``prefix`` into kernel layouts; ``idx`` = positions of (conv3, norm1, conv1x1, norm2,
+    LayerScale) inside the reference's nn.Sequential (they shift when BLSTM / LocalState are inserted, demucs.py:146-149)."""
+    i_c3, i_n1, i_c1, i_n2, i_ls = idx
+    for d in range(depth):
+        p = f"{prefix}.dconv.layers.{d}"
+        put(f"{p}.w1", conv_w(state[f"{p}.{i_c3}.weight"]))
+        put(f"{p}.b1", state[f"{p}.{i_c3}.bias"])
+        put(f"{p}.g1", state[f"{p}.{i_n1}.weight"])
+        put(f"{p}.be1", state[f"{p}.{i_n1}.bias"])
+        put(f"{p}.w2", _interleave_glu(conv_w(state[f"{p}.{i_c1}.weight"])))
+        put(f"{p}.b2", _interleave_glu(state[f"{p}.{i_c1}.bias"].detach().float()))
+        put(f"{p}.g2", _interleave_glu(state[f"{p}.{i_n2}.weight"].detach().float()))
+        put(f"{p}.be2", _interleave_glu(state[f"{p}.{i_n2}.bias"].detach().float()))
+        put(f"{p}.scale", state[f"{p}.{i_ls}.scale"])
+        put(f"{p}.w2t", packed[f"{p}.w2"].cpu().t())      # [hid, 2C] for the dedicated expansion kernels
+        if tc_forms:
+            # tensor-core forms: hidden width padded to a multiple of 16 with zero rows / columns
+            hid = state[f"{p}.{i_c3}.weight"].shape[0]
+            hp = (hid + 15) // 16 * 16
+
+            def pad_rows(t):
+                t = t.detach().float()
+                return torch.cat([t, t.new_zeros((hp - hid,) + tuple(t.shape[1:]))], 0)
+            put(f"{p}.w1p", pad_rows(packed[f"{p}.w1"].cpu()))
+            put(f"{p}.b1p", pad_rows(state[f"{p}.{i_c3}.bias"]))
+            put(f"{p}.g1p", pad_rows(state[f"{p}.{i_n1}.weight"]))
+            put(f"{p}.be1p", pad_rows(state[f"{p}.{i_n1}.bias"]))
+            put(f"{p}.w2p", pad_rows(packed[f"{p}.w2"].cpu().t()).t())
+
+
 class PackedWeights:
     """Reference state_dict -> kernel layouts (one-time, on the device)."""
 
@@ -78,59 +141,8 @@ class PackedWeights:
         def put(name, tensor):
             self.t[name] = tensor.detach().to(device=dev, dtype=torch.float32).contiguous()
 
-        def conv_w(w):  # [Cout, Cin, k(,1)] / [Cout, Cin, kf, kt] -> [Cout, taps*Cin], tap-major
-            w = w.detach().float()
-            co, ci = w.shape[:2]
-            return w.reshape(co, ci, -1).permute(0, 2, 1).reshape(co, -1)
-
-        def convtr_w(w):  # [Cin, Cout, 8(,1)] -> [4*Cout, 2*Cin]; row r*Cout+co, col tap*Cin+ci = w[ci,co,r+4tap]
-            w = w.detach().float()
-            ci, co = w.shape[:2]
-            w = w.reshape(ci, co, 2, 4)                 # k = 4*tap + r
-            return w.permute(3, 1, 2, 0).reshape(4 * co, 2 * ci)
-
-        def convtr_w3(w):
-            """3-tap form of the same transposed conv: output row p = 4 outputs 4p+s, s<4, read x[p-1], x[p], x[p+1]:
-            u = 4p+s+2 = 4*ti + k  =>  tap -1: k=s+6 (s<=1), tap 0: k=s+2, tap +1: k=s-2 (s>=2); other entries zero.
-            Rows = input positions exactly, so tensor-core tiles carry no halo row."""
-            w = w.detach().float()
-            ci, co = w.shape[:2]
-            w = w.reshape(ci, co, 8)
-            out = torch.zeros(4, co, 3, ci)
-            for s_ in range(4):
-                out[s_, :, 1] = w[:, :, s_ + 2].t()
-                if s_ <= 1:
-                    out[s_, :, 0] = w[:, :, s_ + 6].t()
-                else:
-                    out[s_, :, 2] = w[:, :, s_ - 2].t()
-            return out.reshape(4 * co, 3 * ci)
-
         def dconv(prefix):
-            for d in range(cfg.dconv_depth):
-                p = f"{prefix}.dconv.layers.{d}"
-                put(f"{p}.w1", conv_w(state[f"{p}.0.weight"]))
-                put(f"{p}.b1", state[f"{p}.0.bias"])
-                put(f"{p}.g1", state[f"{p}.1.weight"])
-                put(f"{p}.be1", state[f"{p}.1.bias"])
-                put(f"{p}.w2", _interleave_glu(conv_w(state[f"{p}.3.weight"])))
-                put(f"{p}.b2", _interleave_glu(state[f"{p}.3.bias"].detach().float()))
-                put(f"{p}.g2", _interleave_glu(state[f"{p}.4.weight"].detach().float()))
-                put(f"{p}.be2", _interleave_glu(state[f"{p}.4.bias"].detach().float()))
-                put(f"{p}.scale", state[f"{p}.6.scale"])
-                put(f"{p}.w2t", self.t[f"{p}.w2"].cpu().t())      # [hid, 2C] for the dedicated expansion kernels
-                if tc_forms:
-                    # tensor-core forms: hidden width padded to a multiple of 16 with zero rows / columns
-                    hid = state[f"{p}.0.weight"].shape[0]
-                    hp = (hid + 15) // 16 * 16
-
-                    def pad_rows(t):
-                        t = t.detach().float()
-                        return torch.cat([t, t.new_zeros((hp - hid,) + tuple(t.shape[1:]))], 0)
-                    put(f"{p}.w1p", pad_rows(self.t[f"{p}.w1"].cpu()))
-                    put(f"{p}.b1p", pad_rows(state[f"{p}.0.bias"]))
-                    put(f"{p}.g1p", pad_rows(state[f"{p}.1.weight"]))
-                    put(f"{p}.be1p", pad_rows(state[f"{p}.1.bias"]))
-                    put(f"{p}.w2p", pad_rows(self.t[f"{p}.w2"].cpu().t()).t())
+            pack_dconv(put, self.t, state, prefix, cfg.dconv_depth, tc_forms)
 
         for i in range(cfg.depth):
             for name in ("encoder", "tencoder"):

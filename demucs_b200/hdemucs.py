@@ -245,3 +245,87 @@ def init_weights(cfg: HDemucsConfig, seed: int = 0, layer_scale: tp.Optional[flo
     +-1/sqrt(hidden) as nn.LSTM, the LocalState decay projection as demucs.py:181-184: weight * 0.01, bias -2)."""
     from .weights import init_from_specs
     return init_from_specs(param_specs(cfg), seed, layer_scale, cfg.emb_scale)
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _register(root: nn.Module, dotted: str, value: torch.Tensor) -> None:
+    *path, leaf = dotted.split(".")
+    node = root
+    for part in path:
+        if part not in node._modules:
+            node.add_module(part, _Node())
+        node = node._modules[part]
+    node.register_parameter(leaf, nn.Parameter(value, requires_grad=False))
+
+
+class HDemucs(nn.Module):
+    """Hybrid Demucs v3, inference only, on the B200 kernel library.  Constructor keywords, parameter names and
+    ``forward(mix [B, C, T]) -> [B, S, C, T]`` (any T, hdemucs.py:689-794) follow the reference class; extra keyword-only
+    arguments: ``mode`` ("strict" default / "fp32" / ...), ``init_seed`` / ``layer_scale`` (synthetic initialisation)."""
+
+    def __init__(self, sources, *, mode: str = "strict", init_seed: int = 0, layer_scale: tp.Optional[float] = None, **kwargs):
+        super().__init__()
+        self.cfg = HDemucsConfig.from_reference_kwargs(sources=list(sources), **kwargs)
+        self._init_args_kwargs = ((), dict(sources=list(sources), **kwargs))
+        cfg = self.cfg
+        self.sources = list(cfg.sources)
+        self.audio_channels = cfg.audio_channels
+        self.samplerate = cfg.samplerate
+        self.segment = cfg.segment
+        self.nfft, self.hop_length, self.cac, self.depth, self.channels = cfg.nfft, cfg.hop, True, cfg.depth, cfg.channels
+        self.hybrid = True
+        self.mode = mode
+        for name, value in init_weights(cfg, init_seed, layer_scale).items():
+            _register(self, name, value)
+        self._engines: tp.Dict[tp.Tuple, tp.Any] = {}
+        self.train(False)
+
+    @classmethod
+    def from_config(cls, cfg: HDemucsConfig, state=None, mode: str = "strict", init_seed: int = 0,
+                    layer_scale: tp.Optional[float] = None) -> "HDemucs":
+        kw = cfg.reference_kwargs()
+        model = cls(kw.pop("sources"), mode=mode, init_seed=init_seed, layer_scale=layer_scale, **kw)
+        if state is not None:
+            model.load_state_dict(dict(state))
+        return model
+
+    @classmethod
+    def from_reference(cls, module, mode: str = "strict") -> "HDemucs":
+        args, kwargs = module._init_args_kwargs
+        kwargs = dict(kwargs)
+        if args:
+            kwargs["sources"] = args[0]
+        model = cls(kwargs.pop("sources"), mode=mode, **kwargs)
+        model.load_state_dict(module.state_dict())
+        return model
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("demucs_b200.HDemucs is an inference engine; training is out of scope")
+        return super().train(False)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._engines.clear()
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def engine(self):
+        from .hdemucs_engine import HDemucsEngine
+        p = next(self.parameters())
+        key = (p.device, self.mode)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = HDemucsEngine(self.cfg, dict(self.state_dict()), p.device, self.mode)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, mix: torch.Tensor) -> torch.Tensor:
+        return self.engine().forward(mix.float())
+
+
+def hdemucs_mmi(sources=None, **kw) -> HDemucs:
+    """The ``hdemucs_mmi`` architecture with synthetic weights (BASELINE configs[1])."""
+    cfg = hdemucs_mmi_config(sources)
+    return HDemucs.from_config(cfg, **kw)

@@ -215,6 +215,29 @@ int bd_gather_segments(const float* track, float* batch, int B, int C, long long
                        long long length, int seg_first, int nseg_batch, int seg_len, int stride, int valid,
                        void* stream);
 
+/* ---- Hybrid Demucs v3 only (hdemucs.py:123-157,304-335, demucs.py:20-67,157-216) -------------------------------
+ * GroupNorm with G groups over channels-last x [B, rows, C] (norm_groups = 4): sums[(b*G + g)*2 + {0,1}] += (sum, sumsq)
+ * of group g of item b; finish with bd_finalize_group_stats(sums, mean_rstd, B*G, rows*C/G). */
+int bd_gn_stats(const float* x, double* sums, int B, long long rows, int C, int G, void* stream);
+/* y[b*y_item_stride + r*Cout + c] = act(GroupNorm(x)[b, row0 + r, :])[c] (+ addend at the same index, or NULL),
+ * r < rows_out: act BD_ACT_NONE / BD_ACT_GELU keep C channels, BD_ACT_GLU gives C/2 = value[c] * sigmoid(gate[c + C/2])
+ * in the reference's natural channel order.  The row window lets HDecLayer crop AFTER normalising the full transposed-
+ * convolution output (hdemucs.py:326-331); addend carries the next layer's skip connection (hdemucs.py:310). */
+int bd_gn_act(const float* x, float* y, const float* mean_rstd, const float* gamma, const float* beta,
+              const float* addend, int B, long long rows_in, long long row0, long long rows_out, int C, int G, int act,
+              long long y_item_stride, void* stream);
+/* BLSTM frame split (demucs.py:41-47, utils.py:20-35): frames[(b*nframes + k), j, c] = x[b, k*stride + j, c], zero past T. */
+int bd_lstm_frame(const float* x, float* frames, int B, long long T, int C, int nframes, int width, int stride, void* stream);
+/* BLSTM un-framing + skip (demucs.py:52-66): out[b, t] = frames[b*nframes + k(t), t - k(t)*stride] + skip[b, t]. */
+int bd_lstm_unframe_add(const float* frames, const float* skip, float* out, int B, long long T, int C, int nframes, int width,
+                        int stride, void* stream);
+/* One bidirectional nn.LSTM layer from its input projections: pre [N, T, 2, 4H] = x W_ih^T + b_ih + b_hh (direction-major,
+ * gates i f g o), whhT [2, H, 4H] = W_hh transposed, out [N, T, 2H] = [forward | backward], ws >= 6*N*H floats. */
+int bd_lstm_bidir(const float* pre, const float* whhT, float* out, float* ws, int N, int T, int H, void* stream);
+/* LocalState core (demucs.py:186-216, heads x (D/heads), ndecay 4, nfreqs 0): qkc [N, T, 3D] = query | key | content,
+ * dq [N, T, heads*4] decay logits -> out [N, T, D] (before the output projection). */
+int bd_local_state(const float* qkc, const float* dq, float* out, int N, int T, int D, int heads, void* stream);
+
 /* ---- front / back door of the separator (api.py:265-266, audio.py:143-172,175-265) ------------------------------
  * Channel conversion (audio.py:143-166) of x [items, src_ch, len] -> y [items, dst_ch, len]: copy, downmix to mono,
  * replicate mono, or keep the first dst_ch channels. */

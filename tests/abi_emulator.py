@@ -359,6 +359,79 @@ def bd_gather_segments(track, batch, B, Cc, track_len, offset0, length, seg_firs
             out[j][:, lo - start:hi - start] = tr[:, lo:hi]
 
 
+def bd_gn_stats(x, sums, B, rows, Cc, G, stream):
+    v = f32(x, B * rows * Cc).reshape(B, rows, G, Cc // G).astype(np.float64)
+    st = f64(sums, 2 * B * G).reshape(B, G, 2)
+    st[..., 0] += v.sum(axis=(1, 3))
+    st[..., 1] += (v ** 2).sum(axis=(1, 3))
+
+
+def bd_gn_act(x, y, mr, gamma, beta, addend, B, rows_in, row0, rows_out, Cc, G, act, y_item_stride, stream):
+    v = f32(x, B * rows_in * Cc).reshape(B, rows_in, Cc)[:, row0:row0 + rows_out]
+    m = f32(mr, 2 * B * G).reshape(B, G, 2)
+    mean = np.repeat(m[:, :, 0], Cc // G, axis=1)[:, None, :]
+    rstd = np.repeat(m[:, :, 1], Cc // G, axis=1)[:, None, :]
+    v = (v - mean) * rstd * f32(gamma, Cc) + f32(beta, Cc)
+    if act == _lib.ACT_GELU:
+        v = gelu(v)
+    elif act == _lib.ACT_GLU:
+        v = v[..., :Cc // 2] * sigmoid(v[..., Cc // 2:])
+    Co = v.shape[-1]
+    out = f32(y, (B - 1) * y_item_stride + rows_out * Co)
+    add = f32(addend, (B - 1) * y_item_stride + rows_out * Co) if addend else None
+    for b in range(B):
+        sl = slice(b * y_item_stride, b * y_item_stride + rows_out * Co)
+        res = v[b].astype(np.float32).reshape(-1)
+        out[sl] = res + add[sl] if add is not None else res
+
+
+def bd_lstm_frame(x, frames, B, T, Cc, nf, width, stride, stream):
+    v = f32(x, B * T * Cc).reshape(B, T, Cc)
+    pad = np.zeros((B, (nf - 1) * stride + width, Cc), np.float32)
+    pad[:, :T] = v
+    out = f32(frames, B * nf * width * Cc).reshape(B, nf, width, Cc)
+    for k in range(nf):
+        out[:, k] = pad[:, k * stride: k * stride + width]
+
+
+def bd_lstm_unframe_add(frames, skip, out, B, T, Cc, nf, width, stride, stream):
+    fr = f32(frames, B * nf * width * Cc).reshape(B, nf, width, Cc)
+    t = np.arange(T)
+    limit = stride // 2
+    k = np.clip(np.where(t < limit, 0, (t - limit) // stride), 0, nf - 1)
+    f32(out, B * T * Cc).reshape(B, T, Cc)[:] = fr[:, k, t - k * stride] + f32(skip, B * T * Cc).reshape(B, T, Cc)
+
+
+def bd_lstm_bidir(pre, whhT, out, ws, N, T, H, stream):
+    p = f32(pre, N * T * 8 * H).reshape(N, T, 2, 4 * H)
+    w = f32(whhT, 2 * H * 4 * H).reshape(2, H, 4 * H)
+    o = f32(out, N * T * 2 * H).reshape(N, T, 2, H)
+    for d in range(2):
+        h = np.zeros((N, H), np.float32)
+        c = np.zeros((N, H), np.float32)
+        for step in range(T):
+            t = T - 1 - step if d else step
+            g = p[:, t, d] + h @ w[d]
+            i, f, gg, oo = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
+            c = sigmoid(f) * c + sigmoid(i) * np.tanh(gg)
+            h = (sigmoid(oo) * np.tanh(c)).astype(np.float32)
+            o[:, t, d] = h
+
+
+def bd_local_state(qkc, dq, out, N, T, D, heads, stream):
+    v = f32(qkc, N * T * 3 * D).reshape(N, T, 3, heads, D // heads)
+    q, k, c = v[:, :, 0], v[:, :, 1], v[:, :, 2]
+    dots = np.einsum("nthc,nshc->nhts", k, q) / np.sqrt(D // heads)
+    dec = sigmoid(f32(dq, N * T * heads * 4).reshape(N, T, heads, 4)) / 2                    # [n, s, h, f]
+    slope = (dec * (np.arange(1, 5, dtype=np.float32) / 2.0)).sum(-1)                        # [n, s, h]
+    idx = np.arange(T)
+    dots = dots - np.abs(idx[:, None] - idx[None, :])[None, None] * slope.transpose(0, 2, 1)[:, :, None, :]
+    dots[:, :, idx, idx] = -100.0
+    w = np.exp(dots - dots.max(axis=2, keepdims=True))
+    w = w / w.sum(axis=2, keepdims=True)
+    f32(out, N * T * D).reshape(N, T, heads, D // heads)[:] = np.einsum("nhts,nthc->nshc", w, c).astype(np.float32)
+
+
 def _mix_channels(x, src, dst):
     if src == dst or (src > dst and dst != 1):
         return x[:, :dst]
