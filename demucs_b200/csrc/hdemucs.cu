@@ -7,6 +7,7 @@
 //   * LocalState: 4-head attention with learned per-query decay and no self reference.
 // These layers sit on 1/16 .. 1/32 of the time resolution (T <= 336 rows per item): they are latency-, not
 // bandwidth-bound, and are written for clarity in fp32; the convolutions around them go through bd_conv_gemm.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/demucs_b200.h"
 
@@ -124,6 +125,75 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict_
   out[((size_t)b * T + t) * 2 * H + dir * H + u] = h;
 }
 
+// Persistent form of the same recurrence: the launch covers ALL time steps.  A block owns UB hidden units x NB batch
+// items of one direction for the whole sequence; its slice of W_hh (H x 4*UB floats, <= 192 KB) is loaded into shared
+// memory once, the cell state lives in a register, and the only per-step global traffic is the hidden vector exchange:
+// every block publishes its UB units of h_t and the blocks of a direction meet at a counter barrier before reading
+// h_t back (L2-coherent loads).  Launched cooperatively (all blocks co-resident, one per SM); a lost barrier traps.
+template <int UB>
+__global__ void __launch_bounds__(256, 1) lstm_persistent_kernel(const float* __restrict__ pre, const float* __restrict__ whhT,
+                                                                 float* __restrict__ hbuf, unsigned int* __restrict__ bar,
+                                                                 float* __restrict__ out, int N, int T, int H) {
+  constexpr int NB = 256 / UB;
+  extern __shared__ float sh[];
+  float* sW = sh;                                     // [H][4*UB]   (gate-major inside a row)
+  float* sH = sh + (size_t)H * 4 * UB;                // [NB][H]
+  const int dir = blockIdx.z, ul = threadIdx.x % UB, bl = threadIdx.x / UB;
+  const int u = blockIdx.x * UB + ul, b = blockIdx.y * NB + bl;
+  const bool live = u < H && b < N;
+  const unsigned int nblk = gridDim.x * gridDim.y;
+  for (int i = threadIdx.x; i < H * 4 * UB; i += 256) {
+    const int k = i / (4 * UB), r = i - k * 4 * UB, g = r / UB, uu = blockIdx.x * UB + (r - g * UB);
+    sW[i] = uu < H ? __ldg(whhT + ((size_t)dir * H + k) * 4 * H + g * H + uu) : 0.f;
+  }
+  float c = 0.f;
+  for (int step = 0; step < T; ++step) {
+    const int t = dir ? T - 1 - step : step;
+    const float* hprev = hbuf + ((size_t)((step & 1) * 2 + dir) * N) * H;
+    float* hnext = hbuf + ((size_t)(((step + 1) & 1) * 2 + dir) * N) * H;
+    for (int i = threadIdx.x; i < NB * H; i += 256) {
+      const int bb = blockIdx.y * NB + i / H;
+      sH[i] = (bb < N && step > 0) ? __ldcg(hprev + (size_t)bb * H + (i % H)) : 0.f;
+    }
+    __syncthreads();
+    if (live) {
+      const float* hp = sH + bl * H;
+      const float* w = sW + ul;
+      float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
+        const float hk = hp[k];
+        const float* wk = w + (size_t)k * 4 * UB;
+        gi = fmaf(hk, wk[0], gi);
+        gf = fmaf(hk, wk[UB], gf);
+        gg = fmaf(hk, wk[2 * UB], gg);
+        go = fmaf(hk, wk[3 * UB], go);
+      }
+      const float* p = pre + (((size_t)b * T + t) * 2 + dir) * 4 * H + u;
+      gi += __ldg(p); gf += __ldg(p + H); gg += __ldg(p + 2 * H); go += __ldg(p + 3 * H);
+      const float si = 1.f / (1.f + expf(-gi)), sf = 1.f / (1.f + expf(-gf)), so = 1.f / (1.f + expf(-go));
+      c = sf * c + si * tanhf(gg);
+      const float h = so * tanhf(c);
+      __stcg(hnext + (size_t)b * H + u, h);
+      out[((size_t)b * T + t) * 2 * H + dir * H + u] = h;
+    }
+    if (step + 1 < T) {       // all blocks of this direction have published h_t before anyone reads it
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&bar[dir], 1u);
+        const unsigned int want = (unsigned int)(step + 1) * nblk;
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(&bar[dir]) < want) {
+          if (++spins > (1u << 27)) __trap();
+        }
+        __threadfence();
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---- LocalState ----------------------------------------------------------------------------------------------------
 // qkc [N, T, 3*D] = (query | key | content) projections, dq [N, T, heads*4] decay logits, out [N, T, D].
 // One warp per (item, head, query s): scores over all keys t in shared memory, softmax over t, weighted content sum.
@@ -171,6 +241,63 @@ __global__ void __launch_bounds__(128) local_state_kernel(const float* __restric
     float acc = 0.f;
     for (int t = 0; t < T; ++t) acc = fmaf(sc[t], __ldg(ct + (size_t)t * 3 * D), acc);
     out[((size_t)n * T + s) * D + h * dh + c] = acc * r;
+  }
+}
+
+// Same computation with the keys and the content of one (item, head) staged in shared memory once (pitch dh + 1: lanes
+// walk the key axis conflict-free) and the block's 8 warps sharing them across all queries: global traffic drops by T.
+__global__ void __launch_bounds__(256) local_state_tiled_kernel(const float* __restrict__ qkc, const float* __restrict__ dq,
+                                                                float* __restrict__ out, int T, int D, int heads) {
+  extern __shared__ float sh[];
+  const int dh = D / heads, P = dh + 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, n = blockIdx.y;
+  float* sK = sh;                                      // [T][P]
+  float* sC = sK + (size_t)T * P;                      // [T][P]
+  float* sc = sC + (size_t)T * P + (size_t)warp * (T + dh);
+  float* qs = sc + T;
+  const float* base = qkc + (size_t)n * T * 3 * D;
+  for (int i = threadIdx.x; i < T * dh; i += 256) {
+    const int t = i / dh, c = i - t * dh;
+    sK[t * P + c] = __ldg(base + (size_t)t * 3 * D + D + h * dh + c);
+    sC[t * P + c] = __ldg(base + (size_t)t * 3 * D + 2 * D + h * dh + c);
+  }
+  __syncthreads();
+  const float inv = rsqrtf((float)dh);
+  for (int s = warp; s < T; s += 8) {
+    for (int c = lane; c < dh; c += 32) qs[c] = __ldg(base + (size_t)s * 3 * D + h * dh + c);
+    float slope = 0.f;
+    for (int f = 0; f < 4; ++f) {
+      const float d = __ldg(dq + ((size_t)n * T + s) * heads * 4 + h * 4 + f);
+      slope += (float)(f + 1) * 0.5f * (0.5f / (1.0f + expf(-d)));
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) {
+      const float* kt = sK + t * P;
+      float acc = 0.f;
+      for (int c = 0; c < dh; ++c) acc = fmaf(kt[c], qs[c], acc);
+      float v = acc * inv - slope * fabsf((float)(t - s));
+      if (t == s) v = -100.f;
+      sc[t] = v;
+      mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float e = expf(sc[t] - mx);
+      sc[t] = e;
+      sum += e;
+    }
+    sum = bd_warp_sum(sum);
+    __syncwarp();
+    const float r = 1.0f / sum;
+    for (int c = lane; c < dh; c += 32) {
+      float acc = 0.f;
+      for (int t = 0; t < T; ++t) acc = fmaf(sc[t], sC[t * P + c], acc);
+      out[((size_t)n * T + s) * D + h * dh + c] = acc * r;
+    }
+    __syncwarp();
   }
 }
 
@@ -226,6 +353,47 @@ int bd_lstm_bidir(const float* pre, const float* whhT, float* out, float* ws, in
     bd_set_error("bd_lstm_bidir: memset: %s", cudaGetErrorString(e));
     return BD_ERR_CUDA;
   }
+  // persistent form when a block's slice of W_hh fits in shared memory and the grid fits on the device at once
+  const int UB = H <= 192 ? 64 : 32, NB = 256 / UB;
+  const size_t smem = ((size_t)H * 4 * UB + (size_t)NB * H) * sizeof(float);
+  static const bool stepwise = getenv("BD_LSTM_STEPWISE") != nullptr;
+  int dev = 0, sms = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  const int per_chunk = sms / (2 * ((H + UB - 1) / UB));           // batch tiles per launch: grid <= one block per SM
+  if (!stepwise && coop && smem <= 227 * 1024 && per_chunk >= 1) {
+    auto kern = UB == 64 ? lstm_persistent_kernel<64> : lstm_persistent_kernel<32>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      bd_set_error("bd_lstm_bidir: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return BD_ERR_CUDA;
+    }
+    for (int n0 = 0; n0 < N; n0 += per_chunk * NB) {
+      const int n = N - n0 < per_chunk * NB ? N - n0 : per_chunk * NB;
+      const float* pre_c = pre + (size_t)n0 * T * 8 * H;
+      float* out_c = out + (size_t)n0 * T * 2 * H;
+      float* hb = hbuf;                                   // [2][2][n][H] for this chunk (the buffer holds N >= n)
+      unsigned int* bar = reinterpret_cast<unsigned int*>(cbuf);
+      if (n0 > 0) {
+        e = cudaMemsetAsync(cbuf, 0, 2 * sizeof(unsigned int), st);
+        if (e != cudaSuccess) {
+          bd_set_error("bd_lstm_bidir: memset: %s", cudaGetErrorString(e));
+          return BD_ERR_CUDA;
+        }
+      }
+      int nn = n, TT = T, HH = H;
+      void* args[] = {(void*)&pre_c, (void*)&whhT, (void*)&hb, (void*)&bar, (void*)&out_c, (void*)&nn, (void*)&TT, (void*)&HH};
+      const dim3 grid((H + UB - 1) / UB, (n + NB - 1) / NB, 2);
+      e = cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(256), args, smem, st);
+      if (e != cudaSuccess) {
+        bd_set_error("bd_lstm_bidir: cooperative launch (grid %d x %d x 2, %zu B smem): %s", grid.x, grid.y, smem,
+                     cudaGetErrorString(e));
+        return BD_ERR_CUDA;
+      }
+    }
+    return bd_check_launch("lstm_persistent_kernel");
+  }
   const dim3 grid((H + 63) / 64, (N + 3) / 4, 2);
   for (int step = 0; step < T; ++step)
     lstm_step_kernel<<<grid, 256, 4 * H * sizeof(float), st>>>(pre, whhT, hbuf, cbuf, out, N, T, H, step);
@@ -235,6 +403,17 @@ int bd_lstm_bidir(const float* pre, const float* whhT, float* out, float* ws, in
 int bd_local_state(const float* qkc, const float* dq, float* out, int N, int T, int D, int heads, void* stream) {
   BD_REQUIRE(N > 0 && N <= 65535 && T > 0 && D > 0 && heads > 0 && heads <= 65535 && D % heads == 0,
              "bd_local_state: bad sizes (T=%d D=%d heads=%d)", T, D, heads);
+  const int dh = D / heads;
+  const size_t tiled = ((size_t)2 * T * (dh + 1) + (size_t)8 * (T + dh)) * sizeof(float);
+  if (tiled <= 200 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(local_state_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled);
+    if (e != cudaSuccess) {
+      bd_set_error("bd_local_state: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return BD_ERR_CUDA;
+    }
+    local_state_tiled_kernel<<<dim3(heads, N), 256, tiled, (cudaStream_t)stream>>>(qkc, dq, out, T, D, heads);
+    return bd_check_launch("local_state_tiled_kernel");
+  }
   const int smem = 4 * (T + D / heads) * (int)sizeof(float);
   BD_REQUIRE(smem <= 48 * 1024, "bd_local_state: T=%d too long for the shared-memory score rows", T);
   local_state_kernel<<<dim3((T + 3) / 4, heads, N), 128, smem, (cudaStream_t)stream>>>(qkc, dq, out, T, D, heads);

@@ -267,7 +267,7 @@ class HDemucsEngine(Engine):
             self._gemm(M=N * Tt, N=8 * H, Cin=cin, x=cur, w=W[f"{p}.lstm.wih{layer}"], bias=W[f"{p}.lstm.b{layer}"], out=pre)
             out = self._buf(key, f"lstm_out{layer}{tag}", N * Tt * 2 * H)
             self._k("bd_lstm_bidir", ptr(pre), ptr(W[f"{p}.lstm.whhT{layer}"]), ptr(out), ptr(ws), N, Tt, H, st,
-                    flops=16.0 * N * Tt * H * H, nbytes=4.0 * N * Tt * 10 * H, label="lstm_bidir", kernels=Tt)
+                    flops=16.0 * N * Tt * H * H, nbytes=4.0 * N * Tt * 10 * H, label="lstm_bidir")
             cur, cin = out, 2 * H
         if framed:
             lin = self._buf(key, f"lstm_lin{tag}", N * Tt * H)

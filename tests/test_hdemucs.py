@@ -146,3 +146,15 @@ def test_gpu_hdemucs_kernels_match_their_specification():
     dq = torch.randn(N, T, 16, generator=g) - 2
     (got, want), = _both("bd_local_state", lambda d: (qkc.to(d), dq.to(d), torch.zeros(N, T, D, device=d), N, T, D, 4, 0), [2])
     assert rel_l2(got, want) < 2e-6
+    # the shapes of hdemucs_mmi: persistent LSTM with 64 / 32 units per block, several batch chunks; long-T LocalState
+    for N, Tt, H in ((64, 40, 192), (16, 30, 384), (200, 12, 192)):
+        pre = torch.randn(N, Tt, 2, 4 * H, generator=g)
+        whh = torch.randn(2, H, 4 * H, generator=g) / H ** 0.5
+        (got, want), = _both("bd_lstm_bidir", lambda d: (pre.to(d), whh.to(d), torch.zeros(N, Tt, 2 * H, device=d),
+                                                         torch.zeros(6 * N * H, device=d), N, Tt, H, 0), [2])
+        assert rel_l2(got, want) < 3e-6, (N, Tt, H)
+    N, T, D = 1, 1500, 64       # beyond the tiled kernel's shared memory: the streaming form
+    qkc = torch.randn(N, T, 3 * D, generator=g)
+    dq = torch.randn(N, T, 16, generator=g) - 2
+    (got, want), = _both("bd_local_state", lambda d: (qkc.to(d), dq.to(d), torch.zeros(N, T, D, device=d), N, T, D, 4, 0), [2])
+    assert rel_l2(got, want) < 2e-6

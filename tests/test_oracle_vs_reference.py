@@ -57,3 +57,34 @@ def test_apply_model_shifts_and_rng_stream():
         got = apply_model_oracle((W, cfg), mix, shifts=3, overlap=0.3)
     assert random.getstate() == state_ref  # same number of RNG draws
     assert rel_l2(got, want) < 5e-6
+
+
+@pytest.mark.parametrize("length", [343980, 100001])
+def test_hdemucs_oracle_matches_live_reference(length):
+    """Hybrid Demucs v3 (hdemucs.py:689-794): inventory and forward of the oracle against the unmodified reference."""
+    from demucs_b200 import hdemucs as HD
+    from oracle.hdemucs_oracle import hdemucs_forward
+    from oracle.make_golden import hdemucs_small_config, hdemucs_reference
+    cfg = hdemucs_small_config()
+    W = HD.init_weights(cfg, 3, 0.5)
+    model = hdemucs_reference(cfg, W)
+    assert [(k, tuple(v.shape)) for k, v in model.state_dict().items()] == [(k, tuple(s[0])) for k, s in HD.param_specs(cfg).items()]
+    mix = synth_mix(1, length, 9)
+    with torch.no_grad():
+        assert rel_l2(hdemucs_forward(W, cfg, mix), model(mix)) < 2e-6
+
+
+def test_audio_oracle_matches_live_reference():
+    import sys
+    import types
+    refload.load()
+    sys.modules.setdefault("lameenc", types.ModuleType("lameenc"))
+    import demucs.audio as ra
+    from oracle import audio_oracle as O
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 777, generator=g) * 1.5
+    for ch in (1, 2, 3):
+        assert torch.equal(O.convert_audio_channels(x, ch), ra.convert_audio_channels(x, ch))
+    for mode in ("rescale", "clamp", "tanh", "none"):
+        assert torch.equal(O.prevent_clip(x.clone(), mode), ra.prevent_clip(x.clone(), mode))
+    assert torch.equal(O.i16_pcm(x.clone()), ra.i16_pcm(x.clone()))
