@@ -18,6 +18,7 @@ from typing import Callable, Dict, Optional, Tuple, Union
 import torch as th
 
 from .apply import apply_model, BagOfModels, _replace_dict
+from .hdemucs import HDemucs
 from .htdemucs import HTDemucs, htdemucs
 
 
@@ -62,7 +63,7 @@ def list_models(repo: Optional[Path] = None) -> Dict[str, Dict[str, Union[str, P
 class Separator:
     def __init__(
         self,
-        model: Union[str, HTDemucs, BagOfModels] = "htdemucs",
+        model: Union[str, HTDemucs, HDemucs, BagOfModels] = "htdemucs",
         repo: Optional[Path] = None,
         device: str = "cuda" if th.cuda.is_available() else "cpu",
         shifts: int = 1,
@@ -94,7 +95,7 @@ class Separator:
                 setattr(self, "_" + name, value)
 
     def _load_model(self):
-        if isinstance(self._name, (HTDemucs, BagOfModels)):
+        if isinstance(self._name, (HTDemucs, HDemucs, BagOfModels)):
             self._model = self._name
         elif isinstance(self._name, str) and self._name.startswith("synthetic:"):
             self._model = _builtin(self._name[len("synthetic:"):])

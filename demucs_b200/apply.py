@@ -31,9 +31,10 @@ from torch import nn
 
 from . import _lib
 from ._lib import ptr
+from .hdemucs import HDemucs
 from .htdemucs import HTDemucs
 
-Model = HTDemucs
+Model = tp.Union[HTDemucs, HDemucs]
 
 
 class BagOfModels(nn.Module):
@@ -49,8 +50,9 @@ class BagOfModels(nn.Module):
             assert other.sources == first.sources
             assert other.samplerate == first.samplerate
             assert other.audio_channels == first.audio_channels
-            # `segment` only overrides non-HT models in the reference (apply.py:54-56); every model
-            # here is an HTDemucs, whose segment is bound to its training length.
+            if segment is not None:       # apply.py:53-55: overrides the segment of non-HT members, in place
+                if not isinstance(other, HTDemucs) and segment > other.segment:
+                    other.segment = segment
         self.audio_channels = first.audio_channels
         self.samplerate = first.samplerate
         self.sources = first.sources
@@ -171,6 +173,11 @@ def _segment_plan(model: HTDemucs, length: int, split: bool, overlap: float,
         offsets = list(range(0, length, stride))
     else:
         seg_len, stride, offsets = length, length, [0]
+    if not isinstance(model, HTDemucs):
+        # no ``valid_length``: every chunk is evaluated at its own length (apply.py:302-309), so the store is as wide as
+        # the widest chunk and a shorter last chunk is run on its own
+        seg_len = min(seg_len, max(length, 1)) if not split else seg_len
+        return min(seg_len, length), seg_len, stride, offsets
     # leaf: HTDemucs with an explicit segment pads to it, otherwise to the training length
     valid = int(segment * model.samplerate) if segment is not None else train_len
     if min(seg_len, length) > valid or valid > train_len:
@@ -222,7 +229,8 @@ def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor,
     n_slots = max(hi_seg - lo_seg + n_halo, 1)
     key = ("apply", rows, valid)
     segs = eng._buf(key, "segs", n_slots * rows * valid).view(n_slots, rows, valid)
-    if model.cfg.t_layers > 0:
+    fixed = isinstance(model, HTDemucs)          # HTDemucs pads every chunk to one length; v3 runs chunks as they are
+    if fixed and model.cfg.t_layers > 0:
         # the reference draws random.randrange(1) inside every segment forward (transformer.py:680); every
         # rank draws for ALL segments so that sharded ranks keep identical RNG streams
         for _ in range(nseg):
@@ -238,19 +246,29 @@ def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor,
     sent = shard is None
     for s0 in range(lo_seg, hi_seg, batch_size):
         s1 = min(s0 + batch_size, hi_seg)
-        n = s1 - s0
-        batch = eng._buf(key, "batch", n * B * Cc * valid).view(n * B, Cc, valid)
-        eng._k("bd_gather_segments", ptr(track), ptr(batch), B, Cc, Ltrack, ps.offset0, ps.length, s0, n, seg_len, stride,
-               valid, eng._stream(), nbytes=8.0 * n * B * Cc * valid)
         if notify:
             for i in range(s0, s1):
                 notify(offsets[i], "start")
-        eng.forward(batch, out=segs[s0 - lo_seg: s1 - lo_seg])       # [n*B, S, C, valid] = [n, rows, valid]
+        # v3 (no valid_length): the trailing chunks that the window cuts short run one by one at their own length
+        n = s1 - s0 if fixed else sum(1 for i in range(s0, s1) if ps.length - i * stride >= valid)
+        if n > 0:
+            batch = eng._buf(key, "batch", n * B * Cc * valid).view(n * B, Cc, valid)
+            eng._k("bd_gather_segments", ptr(track), ptr(batch), B, Cc, Ltrack, ps.offset0, ps.length, s0, n, seg_len, stride,
+                   valid, eng._stream(), nbytes=8.0 * n * B * Cc * valid)
+            eng.forward(batch, out=segs[s0 - lo_seg: s0 - lo_seg + n])       # [n*B, S, C, valid] = [n, rows, valid]
+        for i in range(s0 + n, s1):
+            # evaluated at its own length and centred in its slot, where the overlap-add's centre trim looks for it
+            n_i = ps.length - i * stride
+            lead = (valid - n_i) // 2
+            one = eng._buf(key, "batch_short", B * Cc * n_i).view(B, Cc, n_i)
+            eng._k("bd_gather_segments", ptr(track), ptr(one), B, Cc, Ltrack, ps.offset0 + i * stride, n_i, 0, 1,
+                   n_i, n_i, n_i, eng._stream(), nbytes=8.0 * B * Cc * n_i)
+            segs[i - lo_seg][:, lead:lead + n_i].copy_(eng.forward(one).view(rows, n_i))
         if notify:
             for i in range(s0, s1):
                 notify(offsets[i], "end")
         if progress_bar is not None:
-            progress_bar.update(n)
+            progress_bar.update(s1 - s0)
         if not sent and s1 >= min(hi_seg, lo_seg + halo):
             # the heads of this block's first segments are ready: ship them to the left neighbours, and post the
             # receives for the heads this block needs from the right

@@ -66,7 +66,7 @@ extern "C" int bd_overlap_add(const float* segs, const float* weight, float* out
                               int nseg, int rows, int valid, int seg_len, int stride, long long length, long long out_ld,
                               long long out_shift, long long n_begin, long long n_end, const float* row_alpha,
                               float alpha, int accumulate, void* stream) {
-  BD_REQUIRE(nseg > 0 && rows > 0 && rows <= 65535 && stride > 0 && seg_len > 0 && seg_len <= valid,
+  BD_REQUIRE(nseg > 0 && rows > 0 && rows <= 65535 && stride > 0 && seg_len > 0 && (seg_len <= valid || length <= valid),
              "bd_overlap_add: bad sizes (nseg=%d rows=%d seg_len=%d valid=%d stride=%d)", nseg, rows, seg_len, valid, stride);
   BD_REQUIRE((long long)(nseg - 1) * stride < length && (long long)nseg * stride >= length,
              "bd_overlap_add: nseg=%d does not tile length=%lld with stride=%d", nseg, length, stride);
@@ -110,7 +110,7 @@ extern "C" int bd_gather_segments(const float* track, float* batch, int B, int C
                                   long long length, int seg_first, int nseg_batch, int seg_len, int stride, int valid,
                                   void* stream) {
   BD_REQUIRE(B > 0 && C > 0 && B * C <= 65535 && nseg_batch > 0 && nseg_batch <= 65535 && valid > 0 && seg_len > 0 &&
-                 seg_len <= valid && stride > 0 && track_len > 0 && length > 0,
+                 (seg_len <= valid || length <= valid) && stride > 0 && track_len > 0 && length > 0,
              "bd_gather_segments: bad sizes");
   BD_REQUIRE((long long)(seg_first + nseg_batch - 1) * stride < length, "bd_gather_segments: segment beyond the window");
   int gx = bd_cdiv(valid, 256 * 4);

@@ -88,7 +88,6 @@ class HDemucsWeights:
                 co, ci = w.shape[:2]
                 z = w.new_zeros(co, ci)
                 put(f"{e}.conv.wpair", torch.cat([z, w[:, :, 0], w[:, :, 1], w[:, :, 2], w[:, :, 3], z], dim=1))
-                put(f"{e}.conv.w", conv_w(w))                                             # general form (odd frame counts)
             pack_dconv(put, self.t, state, e, cfg.dconv_depth, tc_forms, idx)
             if big:
                 hid = state[f"{e}.dconv.layers.0.0.weight"].shape[0]
@@ -307,8 +306,8 @@ class HDemucsEngine(Engine):
         if mix.device != self.device or mix.dtype != torch.float32:
             raise ValueError("mix must be a float32 tensor on the engine's device")
         B, A, L = mix.shape
-        if L < 2 * cfg.nfft:
-            raise ValueError("input shorter than two STFT windows")
+        if L < 2560:     # the reflect padding of _spec (1536 + up to 1023 samples) must stay inside the signal; the
+            raise ValueError("input shorter than 2560 samples: the small-input guard of pad1d (hdemucs.py:29-36) is not built")
         mix = mix.contiguous()
         key = (B, L)
         st = self._stream()
@@ -346,7 +345,7 @@ class HDemucsEngine(Engine):
         xf, Fin, Cin = spec, 2048, 2 * A
         xt, Cin_t = mix, A
         inject = None
-        T5 = (T - 2) // 2 + 1
+        T5 = (T + 1) // 2        # Conv1d(k=4, s=2, p=1) after right-padding T to even
         for l in layers:
             i, Cc = l["index"], l["chout_z"]
             first = i == 0
@@ -409,14 +408,14 @@ class HDemucsEngine(Engine):
             else:
                 rows = T5
                 raw = self._buf(key, f"raw{i}", B * rows * Cc)
-                if T % 2 == 0:
-                    self._gemm(M=B * rows, N=Cc, Cin=2 * Cin, x=xf, w=W[f"{e}.conv.wpair"], bias=W[f"{e}.conv.b"], out=raw,
-                               taps=((0, -1), (0, 0), (0, 1)), I1=1, I0=rows, J1=1, J0=T // 2,
-                               xs=(T * Cin, 0, 2 * Cin, 1), os_=(rows * Cc, 0, Cc))
-                else:
-                    self._gemm(M=B * rows, N=Cc, Cin=Cin, x=xf, w=W[f"{e}.conv.w"], bias=W[f"{e}.conv.b"], out=raw,
-                               taps=tuple((0, k - 1) for k in range(4)), I1=1, I0=rows, m0=2, J1=1, J0=T,
-                               xs=(T * Cin, 0, Cin, 1), os_=(rows * Cc, 0, Cc), tc=False)
+                Tp = T + (T & 1)                  # HEncLayer right-pads the time axis to a multiple of its stride (hdemucs.py:131-135)
+                src = xf
+                if Tp != T:
+                    src = self._buf(key, "z4_padded", B * Tp * Cin, zero=True)
+                    src.view(B, Tp, Cin)[:, :T].copy_(xf.view(B, T, Cin))
+                self._gemm(M=B * rows, N=Cc, Cin=2 * Cin, x=src, w=W[f"{e}.conv.wpair"], bias=W[f"{e}.conv.b"], out=raw,
+                           taps=((0, -1), (0, 0), (0, 1)), I1=1, I0=rows, J1=1, J0=Tp // 2,
+                           xs=(Tp * Cin, 0, 2 * Cin, 1), os_=(rows * Cc, 0, Cc))
             self._gn(key, raw, raw, f"{e}.norm1", B, rows, Cc, _lib.ACT_GELU, tag=f"_e{i}a")
             self._dconv_any(key, e, raw, B, rows, 1, Cc, l, f"_m{i}")
             rw = self._buf(key, f"rw{i}", B * rows * 2 * Cc)

@@ -25,16 +25,18 @@ import yaml
 
 from .apply import BagOfModels
 from .config import UnsupportedConfig
+from .hdemucs import HDemucs, HDemucsConfig
+from .hdemucs import _PINNED as _H_PINNED, _IGNORED as _H_IGNORED
 from .htdemucs import HTDemucs
 
-AnyModel = tp.Union[HTDemucs, BagOfModels]
+AnyModel = tp.Union[HTDemucs, HDemucs, BagOfModels]
 ROOT_URL = "https://dl.fbaipublicfiles.com/demucs/"
 DEFAULT_MODEL = "htdemucs"
 # remote/files.txt + remote/*.yaml of the reference, for the models this engine can run (HTDemucs family)
-REMOTE_FILES = {"955717e8": "hybrid_transformer/955717e8-8726e21a.th", "f7e0c4bc": "hybrid_transformer/f7e0c4bc-ba3fe64a.th",
+REMOTE_FILES = {"75fc33f5": "hybrid_transformer/75fc33f5-1941ce65.th", "955717e8": "hybrid_transformer/955717e8-8726e21a.th", "f7e0c4bc": "hybrid_transformer/f7e0c4bc-ba3fe64a.th",
                 "d12395a8": "hybrid_transformer/d12395a8-e57c48e6.th", "92cfc3b6": "hybrid_transformer/92cfc3b6-ef3bcb9c.th",
                 "04573f0d": "hybrid_transformer/04573f0d-f3cf25b2.th", "5c90dfd2": "hybrid_transformer/5c90dfd2-34c22ccb.th"}
-REMOTE_BAGS = {"htdemucs": {"models": ["955717e8"]},
+REMOTE_BAGS = {"hdemucs_mmi": {"models": ["75fc33f5"]}, "htdemucs": {"models": ["955717e8"]},
                "htdemucs_ft": {"models": ["f7e0c4bc", "d12395a8", "92cfc3b6", "04573f0d"],
                                "weights": [[1., 0., 0., 0.], [0., 1., 0., 0.], [0., 0., 1., 0.], [0., 0., 0., 1.]]},
                "htdemucs_6s": {"models": ["5c90dfd2"]}}
@@ -65,6 +67,8 @@ class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module in ("demucs.htdemucs", "demucs_b200.htdemucs") and name == "HTDemucs":
             return HTDemucs
+        if module in ("demucs.hdemucs", "demucs_b200.hdemucs") and name == "HDemucs":
+            return HDemucs
         if module.startswith("demucs.") or module.startswith("demucs_b200."):
             return _UnsupportedKlass(f"{module}.{name}")
         if (module, name) in _SAFE_GLOBALS:
@@ -80,7 +84,7 @@ class _PickleModule:
     __name__ = "pickle"
 
 
-def load_model(path_or_package, strict: bool = False, mode: str = "strict") -> HTDemucs:
+def load_model(path_or_package, strict: bool = False, mode: str = "strict") -> tp.Union[HTDemucs, HDemucs]:
     """states.py:50-80 -- a model from a serialized package (a dict, or a path to a ``.th`` file)."""
     if isinstance(path_or_package, dict):
         package = path_or_package
@@ -91,23 +95,27 @@ def load_model(path_or_package, strict: bool = False, mode: str = "strict") -> H
     else:
         raise ValueError(f"Invalid type for {path_or_package}.")
     klass, args, kwargs = package["klass"], package["args"], dict(package["kwargs"])
-    if isinstance(klass, _UnsupportedKlass) or not (isinstance(klass, type) and issubclass(klass, HTDemucs)):
+    if isinstance(klass, _UnsupportedKlass) or not (isinstance(klass, type) and issubclass(klass, (HTDemucs, HDemucs))):
         name = getattr(klass, "name", getattr(klass, "__name__", str(klass)))
-        raise ModelLoadingError(f"{name} packages are outside the accelerated path: demucs_b200 runs the HTDemucs family")
+        raise ModelLoadingError(f"{name} packages are outside the accelerated path: demucs_b200 runs HTDemucs (v4) and "
+                                "HDemucs (v3, hdemucs_mmi family) models")
     if args:
         kwargs["sources"] = args[0]
     state = package["state"]
     if state.get("__quantized"):
         raise ModelLoadingError("DiffQ-quantised packages (the *_q models) need the `diffq` package, which is not available")
     if not strict:   # states.py:70-75: drop what the constructor does not know
-        sig = inspect.signature(_reference_kwargs_probe)
+        if issubclass(klass, HDemucs):
+            known = set(_H_PINNED) | set(_H_IGNORED) | set(HDemucsConfig.__dataclass_fields__)
+        else:
+            known = set(inspect.signature(_reference_kwargs_probe).parameters)
         for key in list(kwargs):
-            if key not in sig.parameters:
+            if key not in known:
                 warnings.warn("Dropping inexistant parameter " + key)
                 del kwargs[key]
     sources = kwargs.pop("sources")
     try:
-        model = HTDemucs(sources, mode=mode, **kwargs)
+        model = klass(sources, mode=mode, **kwargs)
     except UnsupportedConfig as err:
         raise ModelLoadingError(str(err)) from err
     model.load_state_dict(state)     # fp16 packages are widened to the fp32 parameters here
@@ -129,12 +137,12 @@ def _reference_kwargs_probe(sources, audio_channels=2, channels=48, channels_tim
     """The reference constructor's signature (htdemucs.py:56-135): what ``load_model(strict=False)`` keeps."""
 
 
-def serialize_model(model: HTDemucs, half: bool = True) -> dict:
+def serialize_model(model: tp.Union[HTDemucs, HDemucs], half: bool = True) -> dict:
     """states.py:118-130 -- the package of a model (fp16 state by default, as the released files)."""
     args, kwargs = model._init_args_kwargs
     dtype = torch.half if half else None
     state = {k: p.data.to(device="cpu", dtype=dtype) for k, p in model.state_dict().items()}
-    return {"klass": HTDemucs, "args": args, "kwargs": kwargs, "state": state, "training_args": {}}
+    return {"klass": type(model), "args": args, "kwargs": kwargs, "state": state, "training_args": {}}
 
 
 def save_with_checksum(content, path: Path) -> Path:

@@ -59,9 +59,14 @@ def apply_single(W, cfg, mix: torch.Tensor, shifts: int, split: bool, overlap: f
     assert transition_power >= 1
     B, C, L = mix.shape
     S = cfg.n_sources
+    is_ht = hasattr(cfg, "t_layers")       # HTDemucs pads to its training length; HDemucs v3 has no valid_length
+    if not is_ht:
+        from .hdemucs_oracle import hdemucs_forward
 
     def leaf(track, offset, length):
         """forward on one centred, zero-padded window of ``track`` (apply.py:302-322)."""
+        if not is_ht:                     # apply.py:306-309: valid_length = length
+            return hdemucs_forward(W, cfg, padded_chunk(track, offset, length, min(track.shape[-1] - offset, length)))
         valid = int(segment * cfg.samplerate) if segment is not None else cfg.segment_length
         if valid < length:
             raise ValueError(f"Given length {length} is longer than training length {valid}")
@@ -86,7 +91,7 @@ def apply_single(W, cfg, mix: torch.Tensor, shifts: int, split: bool, overlap: f
             # is cut from the underlying tensor (apply.py:87-96,108-124)
             sumw[off: off + n] += weight[:n]
             if window is not None and (off + n - out_shift <= window[0] or off - out_shift >= window[1]):
-                if consume_rng and cfg.t_layers > 0:
+                if consume_rng and is_ht and cfg.t_layers > 0:
                     random.randrange(1)
                 continue
             chunk = leaf(track, offset0 + off, n)

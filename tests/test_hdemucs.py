@@ -158,3 +158,25 @@ def test_gpu_hdemucs_kernels_match_their_specification():
     dq = torch.randn(N, T, 16, generator=g) - 2
     (got, want), = _both("bd_local_state", lambda d: (qkc.to(d), dq.to(d), torch.zeros(N, T, D, device=d), N, T, D, 4, 0), [2])
     assert rel_l2(got, want) < 2e-6
+
+
+def test_apply_model_on_hdemucs_host_logic():
+    """apply_model with a v3 model (no ``valid_length``: chunks run at their own length, apply.py:302-312), split with a
+    short last chunk and the shift trick, through the emulated ABI against the oracle's apply."""
+    import random
+    import demucs_b200 as D
+    from oracle.apply_oracle import apply_model_oracle
+    cfg = hdemucs_small_config()
+    cfg.segment = 2.0
+    model = HD.HDemucs.from_config(cfg, init_seed=2, layer_scale=0.5, mode="fp32")
+    W = HD.init_weights(cfg, 2, 0.5)
+    mix = synth_mix(1, 210001, 6)
+    for kw in (dict(shifts=0, overlap=0.25), dict(shifts=1, overlap=0.25), dict(shifts=0, split=False)):
+        m = mix[..., :60000] if kw.get("split") is False else mix
+        with emulated_abi():
+            random.seed(4)
+            got = D.apply_model(model, m.clone(), **kw)
+        random.seed(4)
+        with torch.no_grad():
+            want = apply_model_oracle((W, cfg), m, **kw)
+        assert got.shape == want.shape and rel_l2(got, want) < 2e-5, kw

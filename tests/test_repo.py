@@ -57,19 +57,27 @@ def test_reference_class_reference_is_remapped(tmp_path):
 
 
 def test_unsupported_and_malicious_packages_are_refused(tmp_path):
-    fake_root, fake = types.ModuleType("demucs"), types.ModuleType("demucs.hdemucs")
+    fake_root, fake = types.ModuleType("demucs"), types.ModuleType("demucs.demucs")
 
-    class HDemucs:
+    class Demucs:          # the v1 / v2 time-domain model (members of the mdx bags)
         pass
-    HDemucs.__module__, HDemucs.__qualname__ = "demucs.hdemucs", "HDemucs"
-    fake.HDemucs = HDemucs
-    sys.modules["demucs"], sys.modules["demucs.hdemucs"] = fake_root, fake
+    Demucs.__module__, Demucs.__qualname__ = "demucs.demucs", "Demucs"
+    fake.Demucs = Demucs
+    sys.modules["demucs"], sys.modules["demucs.demucs"] = fake_root, fake
     try:
-        torch.save({"klass": HDemucs, "args": (), "kwargs": {}, "state": {}}, tmp_path / "v3.th")
+        torch.save({"klass": Demucs, "args": (), "kwargs": {}, "state": {}}, tmp_path / "v2.th")
     finally:
-        del sys.modules["demucs"], sys.modules["demucs.hdemucs"]
+        del sys.modules["demucs"], sys.modules["demucs.demucs"]
     with pytest.raises(R.ModelLoadingError, match="outside the accelerated path"):
-        R.load_model(tmp_path / "v3.th")
+        R.load_model(tmp_path / "v2.th")
+    # a Hybrid Demucs v3 package loads into demucs_b200.HDemucs
+    from demucs_b200 import hdemucs as HD
+    from oracle.make_golden import hdemucs_small_config
+    v3 = HD.HDemucs.from_config(hdemucs_small_config(), init_seed=1)
+    path = R.save_with_checksum(R.serialize_model(v3), tmp_path / "cafe0001.th")
+    got = R.LocalRepo(tmp_path).get_model("cafe0001")
+    assert isinstance(got, HD.HDemucs) and got.cfg.dconv_comp == 4
+    assert torch.equal(got.state_dict()["decoder.0.norm2.weight"], v3.state_dict()["decoder.0.norm2.weight"].half().float())
     import os
     torch.save({"klass": os.system, "args": (), "kwargs": {}, "state": {}}, tmp_path / "evil.th")
     with pytest.raises(Exception, match="no use for"):
