@@ -501,7 +501,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("BD_MODE"), choices=["fp32", "tf32", "tf32x3", "strict", "bf16"],
                     help="strict (default): error-compensated tensor-core arithmetic, per-stem rel-L2 <= 1e-4; "
                          "bf16: reduced precision, <= 1e-2")
-    ap.add_argument("--batch", type=int, default=32, help="segments per forward")
+    ap.add_argument("--batch", type=int, default=64, help="segments per forward (64: one forward per step and GPU, ~36 GB)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion run")
     args = ap.parse_args()
