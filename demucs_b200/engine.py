@@ -219,8 +219,18 @@ class Engine:
             return 0
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    MAX_BUFFER_SETS = 6      # activation sets kept alive (one per (batch, length) met); older ones are released
+
     def _buf(self, key, name: str, numel: int, dtype=torch.float32, zero=False) -> torch.Tensor:
-        pool = self._bufs.setdefault(key, {})
+        pool = self._bufs.pop(key, None)
+        if pool is None:
+            # a new geometry (v3 models run every trailing chunk at its own length): drop the least recently used sets
+            # so that a long session does not pin one multi-GB set per distinct length (the caching allocator hands the
+            # memory on in stream order, so queued kernels still see their data)
+            while len(self._bufs) >= self.MAX_BUFFER_SETS:
+                self._bufs.pop(next(iter(self._bufs)))
+            pool = {}
+        self._bufs[key] = pool       # most recently used last
         t = pool.get(name)
         if t is None or t.numel() < numel or t.dtype != dtype:
             t = (torch.zeros if zero else torch.empty)(int(numel), dtype=dtype, device=self.device)

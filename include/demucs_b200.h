@@ -106,7 +106,9 @@ int bd_stft_cac(const float* mix, const float* window, const float* twiddle, flo
                 int B, int A, int L, void* stream);
 /* htdemucs.py:545-554: stats -> norm[b*8 + {0..2}] = (mean, std, 1/(1e-5+std)) of spec, [+4..6] of mix. */
 int bd_finalize_item_norm(const double* stats, float* norm, int B, double n_freq, double n_time, void* stream);
-/* K2a (htdemucs.py:442-471,624-626 + spec.py:30-47): spec [B,T,2048,4S] -> frames [B,S,2,T,4096]. */
+/* K2a / K2b: the two-kernel form of K2 (frames through HBM).  Diagnostic entry points: the engine uses the fused
+ * bd_istft_ola; the parity tests use these to check the inverse FFT and the overlap-add separately.
+ * K2a (htdemucs.py:442-471,624-626 + spec.py:30-47): spec [B,T,2048,4S] -> frames [B,S,2,T,4096]. */
 int bd_istft_frames(const float* spec, const float* norm, const float* window, const float* twiddle, float* frames,
                     int B, int S, int T, void* stream);
 /* K2b (htdemucs.py:449,653-659): out[B,S,2,Lout] = OLA(frames) + xt*stdt + meant; xt [B,Lseg,2S] or NULL. */
@@ -128,7 +130,8 @@ int bd_conv_gemm_arm(const bd_gemm_desc* desc);
  * biased variance, eps 1e-5.  count = elements per slab.  The sums are cleared afterwards, so a buffer that starts
  * at zero needs no fill between one accumulate -> finalize round and the next. */
 int bd_finalize_group_stats(double* sums, float* mean_rstd, int slabs, double count, void* stream);
-/* DConv tail (demucs.py:141-142,151-153): x[m, c] += scale[c] * GLU(GN(u))[m, c]; u [M, 2C] with
+/* DConv tail, diagnostic entry point (the engine fuses it: bd_dconv_expand_update, or the GEMM epilogue)
+ * (demucs.py:141-142,151-153): x[m, c] += scale[c] * GLU(GN(u))[m, c]; u [M, 2C] with
  * interleaved (value, gate) columns; GroupNorm slab of row m =
  * (m / rows_per_item) * slabs_per_item + m % slabs_per_item  (time: 1 slab per item; freq: one per bin). */
 int bd_dconv_tail(float* x, const float* u, const float* mean_rstd, const float* gamma, const float* beta,
@@ -176,7 +179,7 @@ int bd_gn_gelu_apply(float* h, const float* mean_rstd, const float* gamma, const
  * bf16 tensor (it feeds tensor-core GEMMs only). */
 int bd_layer_norm(const float* x, void* y, const float* gamma, const float* beta, const float* pos,
                   int pos_period, long long M, int C, int y_bf16, void* stream);
-/* (sum, sumsq) per item of x [B, n] (for norm_out, transformer.py:372,500). */
+/* (sum, sumsq) per item of x [B, n]: the statistics of a spectrogram handed to forward_core (htdemucs.py:682-692). */
 int bd_item_stats(const float* x, double* sums, int B, long long n, void* stream);
 /* MyGroupNorm(1) apply: x[b, t, c] = (x - mean_b) * rstd_b * gamma[c] + beta[c], in place. */
 int bd_group_norm_apply(float* x, const float* mean_rstd, const float* gamma, const float* beta, int B,
