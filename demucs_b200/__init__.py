@@ -11,6 +11,8 @@ from .htdemucs import HTDemucs, htdemucs  # noqa
 from .apply import apply_model, BagOfModels, TensorChunk, tensor_chunk, center_trim  # noqa
 from .api import Separator, LoadAudioError, LoadModelError, list_models  # noqa
 from .repo import get_model, load_model, ModelLoadingError  # noqa
+from .hdemucs import HDemucs, HDemucsConfig, hdemucs_mmi  # noqa
+from .streaming import StreamSeparator  # noqa
 from ._lib import KernelError  # noqa
 
 __version__ = "0.1.0"

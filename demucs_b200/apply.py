@@ -451,5 +451,10 @@ def apply_model(model: tp.Union[BagOfModels, Model],
         if sink is None:
             sink = _HostSink(out, device)
             sink(*own)
+        elif shard is not None:
+            # the range this rank produced went to the host while it was being made; what a gather policy added
+            # around it ("all", or "root" on rank 0) follows now
+            sink(own[0], shard.produced[0])
+            sink(shard.produced[1], own[1])
         LAST_IO["h2d_bytes"], LAST_IO["d2h_bytes"] = h2d_bytes, sink.bytes
         return sink.finish().view(batch, S, channels, length)

@@ -38,6 +38,7 @@ class Shard:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.owned: tp.Tuple[int, int] = (0, 0)      # output samples this rank holds after the last apply_model
+        self.produced: tp.Tuple[int, int] = (0, 0)   # ... of which it overlap-added these itself (before the gather)
 
     # ---- partitioning -----------------------------------------------------------------------
     def block_of(self, rank: int, nseg: int) -> tp.Tuple[int, int]:
@@ -131,7 +132,7 @@ class Shard:
         from .apply import owned_window
         L = out.shape[-1]
         if self.world == 1:
-            self.owned = (0, L)
+            self.owned = self.produced = (0, L)
             return self.owned
 
         def rng(q, p):
@@ -172,7 +173,7 @@ class Shard:
             for x, y, buf in adds:
                 out[:, x:y] += buf
         a, b = own[self.rank]
-        self.owned = (a, b)
+        self.owned = self.produced = (a, b)
         if self.gather == "none":
             return self.owned
         rows = out.shape[0]

@@ -1,4 +1,2 @@
 cd /root/repo
-CMD="python -m demucs_b200.perf --batch 16 --mode strict --top 5"
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:.*(persist_kernel<\(int\)32, \(int\)256, \(int\)2>|attention_b16_kernel).*' -s 94 -c 7 -o gpurun_out/r02_full_gemm_attn $CMD > gpurun_out/ncu_d.log 2>&1
-ls -la gpurun_out/ | tail -3 >> gpurun_out/ncu_d.log
+timeout 60 python -m pytest tests/test_streaming.py tests/test_gpu_parity.py -q -m gpu -x -k "stream or apply_model_matches or separator_front_door or errors_are_loud" 2>&1 | tail -5 > gpurun_out/r2_last.log
