@@ -123,40 +123,49 @@ class Shard:
             keep.clear()
         return finish
 
+    def pass_range(self, q: int, p: tp.Tuple[int, int, int, int, int], L: int) -> tp.Tuple[int, int]:
+        """Output samples [lo, hi) that rank ``q`` overlap-adds in a pass of geometry ``p``."""
+        from .apply import owned_window
+        nseg, seg_len, stride, length, out_shift = p
+        lo, hi = self.block_of(q, nseg)
+        w0, w1 = owned_window(lo, hi, nseg, seg_len, stride, length)
+        return min(max(w0 - out_shift, 0), L), min(max(w1 - out_shift, 0), L)
+
+    def sliver_schedule(self, passes, L: int):
+        """(own, sched): ownership = the ranges of the first pass (they tile [0, L)); sched = the pieces
+        (sender q, owner r, lo, hi) of what later passes wrote outside the sender's own range.  Pure arithmetic:
+        every rank derives the same schedule."""
+        own = [self.pass_range(q, passes[0], L) for q in range(self.world)]
+        sched = []
+        for q in range(self.world):
+            spans = [self.pass_range(q, p, L) for p in passes]
+            spans = [(a, b) for a, b in spans if b > a]
+            if not spans:
+                continue
+            lo_q, hi_q = min(a for a, _ in spans), max(b for _, b in spans)
+            if own[q][1] <= own[q][0]:          # owns nothing: everything it wrote belongs to somebody else
+                outside = [(lo_q, hi_q)]
+            else:
+                outside = [(lo_q, min(own[q][0], hi_q)), (max(own[q][1], lo_q), hi_q)]
+            for a, b in outside:
+                for r in range(self.world):
+                    x, y = max(a, own[r][0]), min(b, own[r][1])
+                    if r != q and y > x:
+                        sched.append((q, r, x, y))
+        return own, sched
+
     def combine(self, out: torch.Tensor, passes: tp.List[tp.Tuple[int, int, int, int, int]]) -> tp.Tuple[int, int]:
         """``out`` [rows, L] holds what this rank overlap-added in every pass; ``passes`` lists each pass's
         (nseg, seg_len, stride, window length, out_shift), from which every rank derives every rank's sample ranges.
         Ownership = the ranges of the first pass (they tile [0, L)); contributions a later pass wrote outside them are
         sent to their owners and added.  Then the ``gather`` policy.  Returns the range of ``out`` that is valid here.
         """
-        from .apply import owned_window
         L = out.shape[-1]
         if self.world == 1:
             self.owned = self.produced = (0, L)
             return self.owned
 
-        def rng(q, p):
-            nseg, seg_len, stride, length, out_shift = p
-            lo, hi = self.block_of(q, nseg)
-            w0, w1 = owned_window(lo, hi, nseg, seg_len, stride, length)
-            return min(max(w0 - out_shift, 0), L), min(max(w1 - out_shift, 0), L)
-
-        own = [rng(q, passes[0]) for q in range(self.world)]
-        # pieces (sender q -> owner r, [a, b)) of the later passes that landed outside the sender's own range
-        sched = []
-        for q in range(self.world):
-            lo_q = min(rng(q, p)[0] for p in passes if rng(q, p)[1] > rng(q, p)[0]) if any(
-                rng(q, p)[1] > rng(q, p)[0] for p in passes) else own[q][0]
-            hi_q = max((rng(q, p)[1] for p in passes if rng(q, p)[1] > rng(q, p)[0]), default=own[q][1])
-            for a, b in ((lo_q, min(own[q][0], hi_q)), (max(own[q][1], lo_q), hi_q)):
-                if own[q][1] <= own[q][0]:
-                    a, b = lo_q, hi_q                  # a rank that owns nothing gives everything away (once)
-                for r in range(self.world):
-                    if r == q:
-                        continue
-                    x, y = max(a, own[r][0]), min(b, own[r][1])
-                    if y > x and (q, r, x, y) not in sched:
-                        sched.append((q, r, x, y))
+        own, sched = self.sliver_schedule(passes, L)
         ops, keep, adds = [], [], []
         for q, r, x, y in sched:
             if q == self.rank:

@@ -110,3 +110,45 @@ def test_block_partition_and_halo():
     assert all(blocks[i][1] == blocks[i + 1][0] for i in range(7))
     assert Shard.halo(343980, 257985) == 1 and Shard.halo(100, 40) == 2 and Shard.halo(100, 100) == 0
     assert [Fake(r, 4).block(2) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def test_sliver_schedule_routes_every_contribution_to_its_owner():
+    """Pure arithmetic of Shard.combine on the real plans of multi-pass runs (shift trick on 10-minute and short tracks,
+    1..8 ranks): after the scheduled pieces are added, every owner holds exactly one contribution per pass for every
+    sample of its range, ownership tiles the track, and nothing is sent twice."""
+    import numpy as np
+    from demucs_b200.distributed import Shard
+
+    class Fake(Shard):
+        def __init__(self, rank, world):
+            self.rank, self.world, self.group = rank, world, None
+    rng = random.Random(3)
+    seg_len, max_shift = 343980, 22050
+    for world in (1, 2, 3, 8):
+        for L in (26460000 // 40, 3 * 257985 - 1000, 500000, 7 * 257985 + 12345):
+            for overlap in (0.25, 0.6):
+                stride = int((1 - overlap) * seg_len)
+                passes = []
+                for _ in range(3):
+                    offset = rng.randint(0, max_shift)
+                    length = L + max_shift - offset
+                    passes.append((-(-length // stride), seg_len, stride, length, max_shift - offset))
+                sh = Fake(0, world)
+                own, sched = sh.sliver_schedule(passes, L)
+                assert own[0][0] == 0 and own[-1][1] == L or any(b > a for a, b in own)
+                cover = np.zeros(L, np.int32)
+                for a, b in own:
+                    cover[a:b] += 1
+                assert (cover == 1).all()
+                have = [np.zeros(L, np.int32) for _ in range(world)]
+                for q in range(world):
+                    for p in passes:
+                        a, b = sh.pass_range(q, p, L)
+                        have[q][a:b] += 1
+                assert len(set(sched)) == len(sched)
+                got = [h.copy() for h in have]
+                for q, r, x, y in sched:
+                    assert own[r][0] <= x < y <= own[r][1] and not (own[q][0] <= x < own[q][1])
+                    got[r][x:y] += have[q][x:y]
+                for q, (a, b) in enumerate(own):
+                    assert (got[q][a:b] == len(passes)).all(), (world, L, overlap, q)
