@@ -53,8 +53,8 @@ def _single(kwargs, length):
 
 
 @pytest.mark.parametrize("kwargs,length", [
-    (dict(shifts=0, overlap=0.25), 190000),       # 4 segments -> 2 + 2, one halo segment
-    (dict(shifts=1, overlap=0.6), 120000),        # heavy overlap: 2 halo segments, shifted window, RNG in step
+    (dict(shifts=0, overlap=0.25), 160000),       # 4 segments -> 2 + 2, one halo segment
+    (dict(shifts=1, overlap=0.6), 100000),        # heavy overlap: 2 halo segments, shifted window, RNG in step
     (dict(shifts=0, overlap=0.25), 60000),        # one segment on two ranks: rank 1 owns nothing (empty gather piece)
 ])
 def test_sharded_apply_matches_single_process(kwargs, length):
@@ -77,7 +77,7 @@ def test_sharded_apply_matches_single_process(kwargs, length):
 def test_sharded_apply_gather_policies(gather):
     """gather="none": the ranks' owned ranges tile the track and hold the single-process values (shifts=2: the
     ranges of the two passes differ, the slivers travel to their owners); gather="root": rank 0 has everything."""
-    kwargs, length = dict(shifts=2, overlap=0.25), 150000
+    kwargs, length = dict(shifts=2, overlap=0.25), 110000
     ctx = mp.get_context("spawn")
     ret = ctx.SimpleQueue()
     port = 29500 + random.randrange(2000)

@@ -11,7 +11,7 @@ from _fixtures import small_config, synth_mix
 from abi_emulator import emulated_abi
 
 
-@pytest.mark.parametrize("overlap,length", [(0.25, 190000), (0.6, 150000), (0.25, 40000)])
+@pytest.mark.parametrize("overlap,length", [(0.25, 150000), (0.6, 110000), (0.25, 40000)])
 def test_stream_equals_apply_model(overlap, length):
     cfg = small_config()
     model = D.HTDemucs.from_config(cfg, init_seed=0, layer_scale=0.5, mode="fp32")
