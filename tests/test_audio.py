@@ -151,3 +151,31 @@ def test_gpu_separator_resamples_and_emits_pcm():
         w16 = O.i16_pcm(O.prevent_clip(want[i].clone(), "rescale")).t()
         assert pcm[s].dtype == torch.int16 and pcm[s].shape == w16.shape
         assert (pcm[s].int() - w16.int()).abs().float().mean() < 0.6       # quantisation steps, not signal differences
+
+
+def test_separator_front_and_back_door_host_logic():
+    """Separator on a v3 model object with 48 kHz mono input, through the emulated ABI: converted (api.py:265-266),
+    separated, returned as float stems and as int16 frames; against the oracle chain."""
+    import demucs_b200 as D
+    from demucs_b200 import hdemucs as HD
+    from oracle.apply_oracle import apply_model_oracle
+    from oracle.make_golden import hdemucs_small_config
+    cfg = hdemucs_small_config()
+    cfg.segment = 2.0
+    model = HD.HDemucs.from_config(cfg, init_seed=1, layer_scale=0.5, mode="fp32")
+    g = torch.Generator().manual_seed(8)
+    wav48 = 0.3 * torch.randn(1, 60000, generator=g)
+    with emulated_abi():
+        sep = D.Separator(model, device="cpu", shifts=0)
+        _, stems = sep.separate_tensor(wav48.clone(), sr=48000)
+        pcm = sep.separate_tensor_pcm(wav48.clone(), sr=48000, clip="clamp", bits_per_sample=16)
+    wav = O.convert_audio(wav48, 48000, 44100, 2)
+    ref = wav.mean(0)
+    x = (wav - ref.mean()) / (ref.std() + 1e-8)
+    with torch.no_grad():
+        want = apply_model_oracle((HD.init_weights(cfg, 1, 0.5), cfg), x[None], shifts=0)[0]
+    want = want * (ref.std() + 1e-8) + ref.mean()
+    for i, s in enumerate(cfg.sources):
+        assert stems[s].shape == want[i].shape and rel_l2(stems[s], want[i]) < 2e-5
+        w16 = O.i16_pcm(O.prevent_clip(want[i].clone(), "clamp")).t()
+        assert pcm[s].dtype == torch.int16 and (pcm[s].int() - w16.int()).abs().max() <= 1
