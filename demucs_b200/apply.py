@@ -230,6 +230,9 @@ def run_pass(model: HTDemucs, track: torch.Tensor, ps: _Pass, out: torch.Tensor,
     key = ("apply", rows, valid)
     segs = eng._buf(key, "segs", n_slots * rows * valid).view(n_slots, rows, valid)
     fixed = isinstance(model, HTDemucs)          # HTDemucs pads every chunk to one length; v3 runs chunks as they are
+    if shard is not None and not fixed:
+        raise NotImplementedError("sharding across ranks is built for HTDemucs models (fixed-length segments); run v3 "
+                                  "models unsharded, or shard the tracks of a batch across ranks yourself")
     if fixed and model.cfg.t_layers > 0:
         # the reference draws random.randrange(1) inside every segment forward (transformer.py:680); every
         # rank draws for ALL segments so that sharded ranks keep identical RNG streams
