@@ -338,7 +338,10 @@ def gpu_arm(args) -> None:
     top = prof["dominant"]
     # tensor-pipe peak the dominant kernel's MMAs run against: kind::f16 (bf16) for the bf16-operand modes, half of it
     # for kind::tf32.  `achieved` counts ALGORITHMIC flops (2*M*N*K); the split-operand modes issue three MMAs per product.
-    b16 = args.mode in ("strict", "bf16")
+    # ("bf16" mode: only the transformer's kernels -- 64-element k-blocks, attention -- issue bf16 MMAs; its U-Net
+    # convolutions are single-pass tf32)
+    b16 = args.mode == "strict" or (args.mode == "bf16" and (top["name"].startswith("conv_gemm_tc<64") or
+                                                             top["name"].startswith("attention")))
     tensor_peak = peaks["bf16_tflops"] if b16 else peaks["bf16_tflops"] / 2.0
     passes = 3 if args.mode in ("strict", "tf32x3") else 1
     if top["bound"] == "tensor":
