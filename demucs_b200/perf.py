@@ -50,7 +50,7 @@ def main():
     from .htdemucs import htdemucs
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--mode", default="tf32")
+    ap.add_argument("--mode", default="strict")
     ap.add_argument("--top", type=int, default=40)
     args = ap.parse_args()
     model = htdemucs(mode=args.mode).to("cuda")
